@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — inversion frames/sec of the StyleSDF generator hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): FFHQ StyleSDF 256^2 generator pass of the inversion
+loop — G_pred_latents.forward(styles=[w+, w_dec], input_is_latent=True) = 64x64 rays x 24
+samples through the 9-layer FiLM-SIREN + composite, then the modulated-conv decoder to
+256^2 — batch 8 per GPU, synthetic random latents / cameras, random-init weights
+(no checkpoints offline).  One "step" = one such batch.  Weak scaling: every rank runs its
+own batch of 8 and the per-image records are all-gathered once per step.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the
+same through the public module API with pinned-host inputs copied in and the image copied
+out every step.  `--impl reference` times the CPU implementation (the oracle port of the
+reference's PyTorch code; the Python reference itself cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cvpr23-e3dge_b200")
+for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+SIZE, RES, N_SAMPLES, BATCH, SEED = 256, 64, 24, 8, 2024
+METRIC = "inversion frames/sec @256^2 StyleSDF (generator pass: 64x64 rays x 24 samples + decoder)"
+WORKLOAD = ("FFHQ StyleSDF 256^2 inversion, 64 rays x 24 samples, batch=8 per GPU "
+            "(BASELINE.json configs[1])")
+# algorithmic figures per image (SURVEY.md §8d / BASELINE.md §4)
+RENDER_FLOP_PER_IMAGE = 98304 * 526848 * 2
+RENDER_BYTES_PER_IMAGE = 6864896 + 9276  # full dict contract out + styles/camera in
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_generator(device):
+    from helpers import synthetic_state_dict
+    from e3dge_b200 import model_options, rendering_options
+    from e3dge_b200.stylesdf_model import G_pred_latents
+    sd = synthetic_state_dict(SIZE, RES, SEED, "sharp")
+    G = G_pred_latents(model_options(size=SIZE, renderer_spatial_output_dim=RES),
+                       rendering_options(N_samples=N_SAMPLES), full_pipeline=True).eval()
+    G.load_state_dict(sd, strict=True)
+    return G.to(device), sd
+
+
+def make_inputs(rank):
+    from oracle import params as P  # deterministic synthetic latents / cameras (input generator)
+    from helpers import decoder_layout
+    return P.make_inputs(SEED + rank, BATCH, decoder_layout(SIZE, RES), RES)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from e3dge_b200 import _lib, parallel as par
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun "
+                         f"--nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    G, sd = build_generator(dev)
+    host = {k: v.pin_memory() for k, v in make_inputs(rank).items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    n_lat = resident["w_dec"].shape[1]
+    target = torch.zeros(BATCH, 3, SIZE, SIZE, device=dev)
+    rec_local = torch.empty(BATCH, par.record_length(n_lat), device=dev)
+    rec_all = torch.empty(world * BATCH, par.record_length(n_lat), device=dev)
+    img_host = torch.empty(BATCH, 3, SIZE, SIZE).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    def step(inp):
+        with torch.no_grad():
+            out = G([inp["w"], inp["w_dec"]], inp["cam_poses"], inp["focal"], inp["near"],
+                    inp["far"], input_is_latent=True, randomize_noise=True, return_xyz=True,
+                    return_sdf=True)
+            par.pack_records(inp["w"], inp["w_dec"], out["gen_imgs"], target, out=rec_local)
+            if world > 1:
+                par.gather_records(rec_local, out=rec_all, equal_shards=True)
+        return out
+
+    def step_e2e():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out = step(inp)
+        img_host.copy_(out["gen_imgs"], non_blocking=True)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        launches0 = _lib.launch_count
+        for a, b in ev:
+            flush.zero_()  # L2 flush between timed steps, outside the event pair
+            a.record()
+            fn()
+            b.record()
+        sync_all()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), _lib.launch_count - launches0
+
+    with ClockSampler(local) as clk:
+        ms_total, launches = timed(lambda: step(resident), args.steps, args.warmup)
+        ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup))
+    clocks = clk.summary()
+    frames = args.steps * BATCH * world
+    value = frames / (ms_total / 1e3)
+    e2e_value = frames / (ms_e2e / 1e3)
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (random latents/cameras, random-init weights)",
+            "config": {"workload": WORKLOAD, "size": SIZE, "render_res": RES,
+                       "n_samples": N_SAMPLES, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                       "parallelism": f"image-parallel dp{world}, 1 all-gather of latents/metrics per step",
+                       "l2": "256 MiB memset between timed steps, outside the per-step CUDA-event pairs",
+                       "randomize_noise": True},
+            "e2e": {"value": e2e_value, "unit": "frames/s",
+                    "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()),
+                    "d2h_bytes_per_step": img_host.numel() * 4},
+            "gpu_launches": launches, "clocks": clocks}
+
+    if rank == 0:
+        line.update(kernel_roofline(G, resident, dev, flush, args))
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sd, make_inputs(0), steps=2)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(G, inp, dev, flush, args):
+    """Dominant kernel = the fused render kernel; timed alone through the C ABI with CUDA
+    events on the launching stream (after warm-up, L2 flushed between launches)."""
+    from e3dge_b200 import _lib
+    lib = _lib.load()
+    peaks, how = _peaks()
+    R = G.renderer
+    n = max(3, min(args.steps, 10))
+    with torch.no_grad():
+        for _ in range(3):
+            R._render_raw(inp["w"], inp["cam_poses"], inp["focal"], inp["near"], inp["far"])
+        # events bracket only e3_render_fwd: time a second path that re-uses prebuilt buffers
+        film = R._film(inp["w"])  # e3_film_fwd stays outside the bracket
+        times = []
+        for _ in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            R._render_raw(inp["w"], inp["cam_poses"], inp["focal"], inp["near"], inp["far"], film=film)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+    # torch.empty of the outputs is host-side only (caching allocator): the bracket holds 1 kernel
+    ms = statistics.median(times)
+    gbs = RENDER_BYTES_PER_IMAGE * BATCH / (ms / 1e3) / 1e9
+    tflops = RENDER_FLOP_PER_IMAGE * BATCH / (ms / 1e3) / 1e12
+    # measured FP32 FFMA peak of this GPU (register-only probe), the binding roof of this kernel
+    sink = torch.empty(lib.e3_ffma_peak_probe_sink_floats(), device=dev)
+    iters = 20000
+    for _ in range(2):
+        _lib.check(lib.e3_ffma_peak_probe(iters, _lib.ptr(sink), _lib.cur_stream()),
+                   "e3_ffma_peak_probe")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _lib.check(lib.e3_ffma_peak_probe(iters, _lib.ptr(sink), _lib.cur_stream()), "e3_ffma_peak_probe")
+    b.record()
+    torch.cuda.synchronize()
+    ffma_peak = sink.numel() * iters * 16 * 2 / (a.elapsed_time(b) / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "render_kernel_dram_bytes.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    return {"roofline": {"kernel": "siren_render_kernel<0>", "bound": "hbm", "achieved": gbs,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "traffic": traffic, "peak_source": how, "kernel_ms": ms,
+                         "note": "fused renderer is FP32-FFMA-bound by construction (AI ~15 kFLOP/B, "
+                                 "SURVEY.md 8d): the HBM fraction is reported as the metric asks; "
+                                 "the binding roof is `fp32`",
+                         "fp32": {"achieved": tflops, "peak": ffma_peak, "unit": "TFLOP/s",
+                                  "frac": tflops / ffma_peak,
+                                  "peak_source": "measured here (register-only FFMA probe)"}}}
+
+
+def cpu_baseline(sd, inp, steps=2, frames_per_step=BATCH):
+    """The oracle port of the reference's PyTorch code on the host cores (bounded sample)."""
+    from oracle import stylesdf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sl = {k: v[:frames_per_step] for k, v in inp.items()}
+
+    def one():
+        with torch.no_grad():
+            return O.generator_forward(sd, sl["w"], sl["w_dec"], sl["cam_poses"], sl["focal"],
+                                       sl["near"], sl["far"], res=RES, n_samples=N_SAMPLES)
+    one()  # warm-up
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    return {"value": frames_per_step / statistics.median(ts), "unit": "frames/s", "cores": cores,
+            "kind": "port",
+            "sample": f"{steps} timed + 1 warm-up generator passes of {frames_per_step} frame(s) of the "
+                      f"same workload, fp32, torch CPU {torch.__version__}, {cores} threads"}
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from helpers import synthetic_state_dict
+    sd = synthetic_state_dict(SIZE, RES, SEED, "sharp")
+    inp = make_inputs(0)
+    from oracle import stylesdf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sl = {k: v[:1] for k, v in inp.items()}  # bounded sample: one frame of the batch per step
+
+    def one():
+        with torch.no_grad():
+            O.generator_forward(sd, sl["w"], sl["w_dec"], sl["cam_poses"], sl["focal"], sl["near"],
+                                sl["far"], res=RES, n_samples=N_SAMPLES)
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = (f"1 frame of the batch-8 workload per step, fp32, torch CPU {torch.__version__}, "
+              f"{cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (random latents/cameras, random-init weights)",
+        "config": {"workload": WORKLOAD, "size": SIZE, "render_res": RES, "n_samples": N_SAMPLES,
+                   "batch_per_gpu": BATCH},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""In-tree build of the e3dge_b200 C-ABI shared library for sm_100a.
+
+    python cvpr23-e3dge_b200/build.py [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  The .so lands next to the Python binding
+(e3dge_b200/lib/libe3dge_b200.so) so that it travels to the GPU box with the snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "e3dge_b200", "lib")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB = os.path.join(OUT_DIR, "libe3dge_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+         "--expt-relaxed-constexpr"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in sorted(os.listdir(root)):
+            with open(os.path.join(root, f), "rb") as fh:
+                h.update(f.encode())
+                h.update(fh.read())
+    h.update(" ".join(ARCH + FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+    cmd = [NVCC, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    with open(os.path.join(OBJ_DIR, src[:-3] + ".ptxas.log"), "w") as fh:
+        fh.write(log)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{log}")
+    if verbose:
+        print(log)
+    return obj
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    stamp = os.path.join(OUT_DIR, "build.sha256")
+    dig = _digest()
+    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read() == dig:
+        return LIB
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), sources()))
+    cmd = [NVCC, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", LIB, *objs]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    with open(stamp, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,113 @@
+// Shared device/host helpers for the e3dge_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/e3dge_b200.h"
+
+namespace e3 {
+
+// ---- host-side error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define E3_REQUIRE(cond, code, ...)          \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::e3::set_error(__VA_ARGS__);          \
+      return (code);                         \
+    }                                        \
+  } while (0)
+
+#define E3_CUDA(call)                                        \
+  do {                                                       \
+    int _rc = ::e3::check_cuda((call), #call);               \
+    if (_rc != 0) return _rc;                                \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+// ---- device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src,
+                                             uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// sin(x) accurate to <= 1.5 ulp for |x| < 2^15: 3-term Cody-Waite reduction to
+// [-pi/4, pi/4] + minimax polynomials.  FiLM pre-activations reach |x| ~ 1e2, where
+// sin.approx (MUFU) does not hold the 1e-3 end-to-end parity bar.
+__device__ __forceinline__ float sin_accurate(float a) {
+  float j = fmaf(a, 0.636619747f, 12582912.0f);  // rint(a * 2/pi) via the 1.5*2^23 trick
+  const int q = __float_as_int(j);
+  j -= 12582912.0f;
+  float r = fmaf(j, -1.57079601e+00f, a);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float s = r * r;
+  float ps = fmaf(-1.9515295891e-4f, s, 8.3321608736e-3f);
+  ps = fmaf(ps, s, -1.6666654611e-1f);
+  ps = fmaf(ps * s, r, r);
+  float pc = fmaf(2.443315711809948e-5f, s, -1.388731625493765e-3f);
+  pc = fmaf(pc, s, 4.166664568298827e-2f);
+  pc = fmaf(pc, s, -0.5f);
+  pc = fmaf(pc, s, 1.0f);
+  float res = (q & 1) ? pc : ps;
+  return (q & 2) ? -res : res;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace e3

@@ -1,0 +1,564 @@
+// Modulated-conv StyleGAN2 decoder kernels (channels-last fp32 activations).
+//
+// Replaces ModulatedConv2d / StyledConv / ToRGB / NoiseInjection / Blur / Upsample of
+//   project/models/stylesdf_model.py:263-362, 365-466, 469-541, 96-165
+// (arithmetic spec: SURVEY.md Appendix A.7).
+//
+// Formulation.  The reference builds per-sample weights W'[b,o,i,k] = scale*W[o,i,k]*s[b,i]
+// * d[b,o] and runs a grouped conv with groups = batch.  Here the modulation is moved onto
+// the activations and the demodulation onto the output:
+//     y[b,o] = d[b,o] * conv(x[b,i] * s[b,i], scale*W[o,i])
+// so one shared weight matrix serves the whole batch (a plain implicit GEMM), and
+// d[b,o] = rsqrt(scale^2 * sum_i s[b,i]^2 * sum_k W[o,i,k]^2 + 1e-8) is a tiny GEMV.
+// The upsampling conv (conv_transpose2d stride 2, then the 4x4 [1,3,3,1] blur) is computed
+// at its minimum FLOP count: a 1x1-style GEMM  G[pix, (ky,kx,o)] = sum_i xs[pix,i] *
+// W[o,i,ky,kx]  followed by a fused col2im + blur + noise + bias + leaky-ReLU gather.
+//
+// This file is the fp32 CUDA-core (FFMA) implementation: exact-fp32 arithmetic, used for
+// parity and as the numerical baseline of the tcgen05 path.
+#include "common.cuh"
+
+namespace e3 {
+
+constexpr float kSqrt2 = 1.41421356237309515f;
+
+// ---- weight preparation -----------------------------------------------------------------
+__global__ void weight_sq_kernel(const float* __restrict__ w, int n_oi, int kk, float* __restrict__ wsq) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_oi) return;
+  float acc = 0.f;
+  for (int k = 0; k < kk; ++k) {
+    const float v = w[(size_t)idx * kk + k];
+    acc = fmaf(v, v, acc);
+  }
+  wsq[idx] = acc;
+}
+
+// plain:    Wg[tap][ci][o]        = scale * W[o][ci][tap]
+// upsample: Wg[ci][tap*cout + o]  = scale * W[o][ci][tap]
+__global__ void conv_pack_kernel(const float* __restrict__ w, int cout, int cin, int upsample,
+                                 float scale, float* __restrict__ wg) {
+  const int64_t total = (int64_t)cout * cin * 9;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int o, ci, tap;
+    if (upsample) {
+      o = (int)(idx % cout);
+      tap = (int)((idx / cout) % 9);
+      ci = (int)(idx / ((int64_t)cout * 9));
+    } else {
+      o = (int)(idx % cout);
+      ci = (int)((idx / cout) % cin);
+      tap = (int)(idx / ((int64_t)cout * cin));
+    }
+    wg[idx] = scale * w[((size_t)o * cin + ci) * 9 + tap];
+  }
+}
+
+// s[b,i] = (mod_w[i,:] . latent[b,:]) / sqrt(512) + mod_b[i]   (EqualLinear, stylesdf_model.py:234-244)
+__global__ void __launch_bounds__(256) mod_style_kernel(const float* __restrict__ latent,
+                                                        int64_t latent_stride,
+                                                        const float* __restrict__ mod_w,
+                                                        const float* __restrict__ mod_b, int cin,
+                                                        float* __restrict__ s) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= cin) return;
+  const float* lat = latent + (size_t)b * latent_stride;
+  float acc = 0.f;
+  for (int j = lane; j < 512; j += 32) acc = fmaf(mod_w[(size_t)i * 512 + j], lat[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) s[(size_t)b * cin + i] = acc * 0.04419417382415922f + mod_b[i];  // 1/sqrt(512)
+}
+
+// d[b,o] = rsqrt(scale^2 * sum_i wsq[o,i] * s[b,i]^2 + 1e-8)   (stylesdf_model.py:321-326)
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ wsq,
+                                                    const float* __restrict__ s, int cin, int cout,
+                                                    float scale2, float* __restrict__ d) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= cout) return;
+  float acc = 0.f;
+  for (int i = lane; i < cin; i += 32) {
+    const float sv = s[(size_t)b * cin + i];
+    acc = fmaf(wsq[(size_t)o * cin + i], sv * sv, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) d[(size_t)b * cout + o] = rsqrtf(fmaf(scale2, acc, 1e-8f));
+}
+
+// ---- implicit-GEMM conv on the FFMA pipe ---------------------------------------------------
+// C[m][n] = sum_{tap,ci} (x[b, y+dy, x+dx, ci] * s[b,ci]) * Wg[tap][ci][n],  m = (b,y,x)
+// 128x128 tile, BK = 16, 256 threads, 8x8 register tile, register-staged double buffering.
+struct ConvGemmArgs {
+  const float* x;   // [B,H,W,Cin]
+  const float* s;   // [B,Cin]
+  const float* wg;  // [TAPS][Cin][N]
+  float* out;       // [M][N]
+  int B, H, W, Cin, N;
+  // epilogue: mode 0 raw store; 1 lrelu(d*acc + noise_w*noise + bias)*sqrt2; 2 d*acc
+  int mode;
+  const float* d;         // [B,N]
+  const float* noise;     // [H*W] (+ b*noise_bstride)
+  int64_t noise_bstride;
+  const float* noise_w;   // [1]
+  const float* act_bias;  // [N]
+};
+
+constexpr int CG_BM = 128, CG_BN = 128, CG_BK = 16, CG_LDA = CG_BM + 4;
+
+template <int TAPS>
+__global__ void __launch_bounds__(256, 2) conv_gemm_ffma_kernel(const __grid_constant__ ConvGemmArgs a) {
+  __shared__ __align__(16) float As[2][CG_BK][CG_LDA];
+  __shared__ __align__(16) float Bs[2][CG_BK][CG_BN];
+  const int tid = threadIdx.x;
+  const int tn = tid & 15, tm = tid >> 4;
+  const int HW = a.H * a.W;
+  const int64_t M = (int64_t)a.B * HW;
+  const int64_t m0 = (int64_t)blockIdx.x * CG_BM;
+  const int n0 = blockIdx.y * CG_BN;
+  const int k_chunks_per_tap = a.Cin / CG_BK;
+  const int n_chunks = TAPS * k_chunks_per_tap;
+
+  // A-gather role: one pixel row per thread, 8 channels
+  const int ar = tid & 127, ah = tid >> 7;
+  const int64_t am = m0 + ar;
+  const bool a_row_ok = am < M;
+  int ab = 0, ay = 0, ax = 0;
+  if (a_row_ok) {
+    ab = (int)(am / HW);
+    const int p = (int)(am - (int64_t)ab * HW);
+    ay = p / a.W;
+    ax = p - ay * a.W;
+  }
+  float4 ra[2], rb[2];
+
+  auto load_chunk = [&](int kc) {
+    const int tap = kc / k_chunks_per_tap;
+    const int ci0 = (kc - tap * k_chunks_per_tap) * CG_BK + ah * 8;
+    int yy = ay, xx = ax;
+    if (TAPS == 9) {
+      yy += tap / 3 - 1;
+      xx += tap % 3 - 1;
+    }
+    ra[0] = ra[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a_row_ok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+      const float4* src =
+          reinterpret_cast<const float4*>(a.x + (((size_t)ab * a.H + yy) * a.W + xx) * a.Cin + ci0);
+      const float4* sp = reinterpret_cast<const float4*>(a.s + (size_t)ab * a.Cin + ci0);
+      const float4 v0 = src[0], v1 = src[1], s0 = sp[0], s1 = sp[1];
+      ra[0] = make_float4(v0.x * s0.x, v0.y * s0.y, v0.z * s0.z, v0.w * s0.w);
+      ra[1] = make_float4(v1.x * s1.x, v1.y * s1.y, v1.z * s1.z, v1.w * s1.w);
+    }
+    const float* wrow = a.wg + ((size_t)tap * a.Cin + (kc - tap * k_chunks_per_tap) * CG_BK) * a.N;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = tid + 256 * j, row = f >> 5, c4 = (f & 31) * 4;
+      rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + c4 < a.N) rb[j] = *reinterpret_cast<const float4*>(wrow + (size_t)row * a.N + n0 + c4);
+    }
+  };
+  auto store_chunk = [&](int buf) {
+    const float v[8] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) As[buf][ah * 8 + k][ar] = v[k];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = tid + 256 * j, row = f >> 5, c4 = (f & 31) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][row][c4]) = rb[j];
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < n_chunks) load_chunk(kc + 1);
+#pragma unroll
+    for (int k = 0; k < CG_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tn * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kc + 1 < n_chunks) {
+      store_chunk(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+  const float nw = (a.mode == 1) ? a.noise_w[0] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + tm * 8 + i;
+    if (m >= M) continue;
+    const int b = (int)(m / HW);
+    const int p = (int)(m - (int64_t)b * HW);
+    const float nz = (a.mode == 1) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + h * 64 + tn * 4;
+      if (n >= a.N) continue;
+      float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
+      if (a.mode == 1) {
+        const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.N + n);
+        const float4 bv = *reinterpret_cast<const float4*>(a.act_bias + n);
+        const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float t = fmaf(v[q], dd[q], nz) + bb[q];
+          v[q] = (t > 0.f ? t : 0.2f * t) * kSqrt2;
+        }
+      } else if (a.mode == 2) {
+        const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.N + n);
+        v[0] *= dv.x, v[1] *= dv.y, v[2] *= dv.z, v[3] *= dv.w;
+      }
+      *reinterpret_cast<float4*>(a.out + (size_t)m * a.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// ---- col2im (stride-2 transposed conv scatter, as a gather) + 4x4 blur + StyledConv epilogue ----
+// T[P,Q,o]  = sum_{ky,kx : P-ky, Q-kx even, in range} G[(P-ky)/2, (Q-kx)/2, ky, kx, o]   (P,Q in [0,2H])
+// out[Y,X,o] = lrelu( d * sum_{a,c<4} kb[a] kb[c] T[Y+a-1, X+c-1, o] + noise + bias ) * sqrt2,
+// kb = [1,3,3,1]/4  (blur kernel outer([1,3,3,1])/64 * 4, pad (1,1); stylesdf_model.py:283-291,339-346)
+struct Col2imArgs {
+  const float* g;  // [B,H,W,9,cout]
+  float* y;        // [B,2H,2W,cout]
+  int B, H, W, cout;
+  const float* d;
+  const float* noise;
+  int64_t noise_bstride;
+  const float* noise_w;
+  const float* act_bias;  // NULL: bare modulated conv (d * blur(convT)), no noise / bias / act
+};
+
+__global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_constant__ Col2imArgs a) {
+  const int c4n = a.cout >> 2;
+  const int OH = 2 * a.H, OW = 2 * a.W;
+  const int64_t total = (int64_t)a.B * OH * OW * c4n;
+  const bool linear = a.act_bias == nullptr;
+  const float nw = linear ? 0.f : a.noise_w[0];
+  const float kb[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % c4n) * 4;
+    int64_t t = idx / c4n;
+    const int X = (int)(t % OW);
+    t /= OW;
+    const int Y = (int)(t % OH);
+    const int b = (int)(t / OH);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ay = 0; ay < 4; ++ay) {
+      const int P = Y + ay - 1;
+      if (P < 0 || P > OH) continue;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ry = P - ky;
+        if (ry < 0 || (ry & 1)) continue;
+        const int iy = ry >> 1;
+        if (iy >= a.H) continue;
+#pragma unroll
+        for (int ax = 0; ax < 4; ++ax) {
+          const int Q = X + ax - 1;
+          if (Q < 0 || Q > OW) continue;
+          const float wgt = kb[ay] * kb[ax];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int rx = Q - kx;
+            if (rx < 0 || (rx & 1)) continue;
+            const int ix = rx >> 1;
+            if (ix >= a.W) continue;
+            const float4 gv = *reinterpret_cast<const float4*>(
+                a.g + ((((size_t)b * a.H + iy) * a.W + ix) * 9 + ky * 3 + kx) * a.cout + o);
+            acc.x = fmaf(wgt, gv.x, acc.x), acc.y = fmaf(wgt, gv.y, acc.y);
+            acc.z = fmaf(wgt, gv.z, acc.z), acc.w = fmaf(wgt, gv.w, acc.w);
+          }
+        }
+      }
+    }
+    const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);
+    float v[4] = {acc.x * dv.x, acc.y * dv.y, acc.z * dv.z, acc.w * dv.w};
+    if (!linear) {
+      const float nz = nw * a.noise[(size_t)b * a.noise_bstride + (size_t)Y * OW + X];
+      const float4 bv = *reinterpret_cast<const float4*>(a.act_bias + o);
+      v[0] = fmaf(acc.x, dv.x, nz) + bv.x, v[1] = fmaf(acc.y, dv.y, nz) + bv.y;
+      v[2] = fmaf(acc.z, dv.z, nz) + bv.z, v[3] = fmaf(acc.w, dv.w, nz) + bv.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (v[q] > 0.f ? v[q] : 0.2f * v[q]) * kSqrt2;
+    }
+    *reinterpret_cast<float4*>(a.y + (((size_t)b * OH + Y) * OW + X) * a.cout + o) =
+        make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ---- ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip ----------------------
+struct ToRgbArgs {
+  const float* x;     // [B,H,W,cin]
+  const float* w;     // [3,cin]
+  const float* s;     // [B,cin]
+  const float* bias;  // [3]
+  const float* skip;  // NULL | [B,3,H/2,W/2] | [B,3,H,W]
+  int upsample_skip;
+  float* rgb;  // [B,3,H,W]
+  int B, H, W, cin;
+};
+
+__global__ void __launch_bounds__(256) torgb_kernel(const __grid_constant__ ToRgbArgs a) {
+  extern __shared__ float ws[];  // [3][cin] = scale * W[c,i] * s[b,i]
+  const int b = blockIdx.y, HW = a.H * a.W;
+  const float scale = rsqrtf((float)a.cin);  // 1/sqrt(cin*1*1)
+  for (int i = threadIdx.x; i < 3 * a.cin; i += blockDim.x)
+    ws[i] = scale * a.w[i] * a.s[(size_t)b * a.cin + (i % a.cin)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float kb[4] = {0.25f, 0.75f, 0.75f, 0.25f};  // flipped == itself (symmetric)
+  for (int p = blockIdx.x * 8 + warp; p < HW; p += gridDim.x * 8) {
+    const float* xp = a.x + ((size_t)b * HW + p) * a.cin;
+    float r = 0.f, g = 0.f, bl = 0.f;
+    for (int i = lane * 4; i < a.cin; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + i);
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + i);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + a.cin + i);
+      const float4 w2 = *reinterpret_cast<const float4*>(ws + 2 * a.cin + i);
+      r = fmaf(v.x, w0.x, fmaf(v.y, w0.y, fmaf(v.z, w0.z, fmaf(v.w, w0.w, r))));
+      g = fmaf(v.x, w1.x, fmaf(v.y, w1.y, fmaf(v.z, w1.z, fmaf(v.w, w1.w, g))));
+      bl = fmaf(v.x, w2.x, fmaf(v.y, w2.y, fmaf(v.z, w2.z, fmaf(v.w, w2.w, bl))));
+    }
+    r = warp_sum(r), g = warp_sum(g), bl = warp_sum(bl);
+    if (lane < 3) {
+      const int c = lane;
+      float v = (c == 0 ? r : (c == 1 ? g : bl)) + a.bias[c];
+      if (a.skip) {
+        const int Y = p / a.W, X = p - Y * a.W;
+        if (a.upsample_skip) {
+          // upfirdn2d(skip, outer(kb,kb), up=2, pad=(2,1)): U[2i]=skip[i]; P[y]=U[y-2]
+          const int h2 = a.H >> 1, w2 = a.W >> 1;
+          const float* sp = a.skip + ((size_t)b * 3 + c) * h2 * w2;
+          float up = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky) {
+            const int uy = Y + ky - 2;
+            if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              const int ux = X + kx - 2;
+              if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
+              up = fmaf(sp[(size_t)(uy >> 1) * w2 + (ux >> 1)], kb[3 - ky] * kb[3 - kx], up);
+            }
+          }
+          v += up;
+        } else {
+          v += a.skip[((size_t)b * 3 + c) * HW + p];
+        }
+      }
+      a.rgb[((size_t)b * 3 + c) * HW + p] = v;
+    }
+  }
+}
+
+// ---- image-parallel inversion record ----------------------------------------
+__global__ void __launch_bounds__(256) pack_record_kernel(const float* __restrict__ w_plus,
+                                                          const float* __restrict__ w_dec,
+                                                          int n_latent, const float* __restrict__ image,
+                                                          const float* __restrict__ target,
+                                                          int64_t image_numel,
+                                                          float* __restrict__ record) {
+  const int b = blockIdx.x;
+  const int rec_len = 2304 + n_latent * 512 + 2;
+  float* rec = record + (size_t)b * rec_len;
+  for (int i = threadIdx.x; i < 2304; i += blockDim.x) rec[i] = w_plus[(size_t)b * 2304 + i];
+  for (int i = threadIdx.x; i < n_latent * 512; i += blockDim.x)
+    rec[2304 + i] = w_dec[(size_t)b * n_latent * 512 + i];
+  float se = 0.f, ae = 0.f;
+  if (image && target) {
+    const float* im = image + (size_t)b * image_numel;
+    const float* tg = target + (size_t)b * image_numel;
+    for (int64_t i = threadIdx.x; i < image_numel; i += blockDim.x) {
+      const float dlt = im[i] - tg[i];
+      se = fmaf(dlt, dlt, se);
+      ae += fabsf(dlt);
+    }
+  }
+  __shared__ float red[2][8];
+  se = warp_sum(se), ae = warp_sum(ae);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[0][warp] = se, red[1][warp] = ae;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s2 = 0.f, a2 = 0.f;
+    for (int i = 0; i < 8; ++i) s2 += red[0][i], a2 += red[1][i];
+    rec[rec_len - 2] = s2 / (float)image_numel;
+    rec[rec_len - 1] = a2 / (float)image_numel;
+  }
+}
+
+static int grid_cap(int64_t blocks) {
+  const int64_t cap = (int64_t)sm_count() * 32;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace e3
+
+using namespace e3;
+
+extern "C" int e3_modconv_weight_sq(const float* weight, int cout, int cin, int ksize, float* wsq,
+                                    void* stream) {
+  E3_REQUIRE(weight && wsq && cout > 0 && cin > 0 && ksize > 0, E3_ERR_BAD_ARG,
+             "e3_modconv_weight_sq: bad argument");
+  const int n = cout * cin;
+  weight_sq_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(weight, n, ksize * ksize, wsq);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" int e3_modconv_styles(const float* latent, int64_t latent_stride, const float* mod_w,
+                                 const float* mod_b, const float* wsq, int batch, int cin, int cout,
+                                 int ksize, float* s, float* d, void* stream) {
+  E3_REQUIRE(latent && mod_w && mod_b && s, E3_ERR_BAD_ARG, "e3_modconv_styles: null argument");
+  E3_REQUIRE(batch >= 0 && cin > 0 && batch <= 65535, E3_ERR_BAD_ARG, "e3_modconv_styles: bad shape");
+  E3_REQUIRE(!d || (wsq && cout > 0 && ksize > 0), E3_ERR_BAD_ARG,
+             "e3_modconv_styles: demodulation needs wsq, cout, ksize");
+  if (batch == 0) return E3_OK;
+  mod_style_kernel<<<dim3((cin + 7) / 8, batch), 256, 0, as_stream(stream)>>>(latent, latent_stride,
+                                                                           mod_w, mod_b, cin, s);
+  if (d) {
+    const float scale2 = 1.f / (float)(cin * ksize * ksize);
+    demod_kernel<<<dim3((cout + 7) / 8, batch), 256, 0, as_stream(stream)>>>(wsq, s, cin, cout,
+                                                                          scale2, d);
+  }
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" size_t e3_conv_packed_bytes(int cout, int cin) {
+  return (size_t)cout * cin * 9 * sizeof(float);
+}
+
+extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample,
+                                   void* packed, void* stream) {
+  E3_REQUIRE(weight && packed && cout > 0 && cin > 0, E3_ERR_BAD_ARG, "e3_conv_pack_weight: bad argument");
+  const float scale = 1.f / sqrtf((float)(cin * 9));
+  conv_pack_kernel<<<grid_cap(((int64_t)cout * cin * 9 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      weight, cout, cin, upsample, scale, static_cast<float*>(packed));
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout,
+                                               int upsample) {
+  (void)cin;
+  return upsample ? (size_t)batch * h * w * 9 * cout * sizeof(float) : 0;
+}
+
+static int check_conv_shapes(const char* who, int batch, int h, int w, int cin, int cout) {
+  E3_REQUIRE(batch >= 0 && h > 0 && w > 0, E3_ERR_BAD_ARG, "%s: bad shape", who);
+  E3_REQUIRE(cin % 16 == 0 && cout % 4 == 0, E3_ERR_UNSUPPORTED,
+             "%s: needs cin %% 16 == 0 and cout %% 4 == 0 (got cin=%d cout=%d)", who, cin, cout);
+  return E3_OK;
+}
+
+extern "C" int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const float* s,
+                                     const float* d, const float* noise, int64_t noise_batch_stride,
+                                     const float* noise_w, const float* act_bias, float* y, int batch,
+                                     int h, int w, int cin, int cout, void* scratch,
+                                     size_t scratch_bytes, void* stream) {
+  (void)scratch;
+  (void)scratch_bytes;
+  int rc = check_conv_shapes("e3_styled_conv3x3_fwd", batch, h, w, cin, cout);
+  if (rc) return rc;
+  if (batch == 0) return E3_OK;
+  E3_REQUIRE(x && wpacked && s && d && y, E3_ERR_BAD_ARG, "e3_styled_conv3x3_fwd: null argument");
+  E3_REQUIRE(!act_bias || (noise && noise_w), E3_ERR_BAD_ARG,
+             "e3_styled_conv3x3_fwd: noise and noise_w are required unless act_bias is NULL");
+  ConvGemmArgs a{};
+  a.x = x, a.s = s, a.wg = static_cast<const float*>(wpacked), a.out = y;
+  a.B = batch, a.H = h, a.W = w, a.Cin = cin, a.N = cout;
+  a.mode = act_bias ? 1 : 2, a.d = d, a.noise = noise, a.noise_bstride = noise_batch_stride;
+  a.noise_w = noise_w, a.act_bias = act_bias;
+  const int64_t M = (int64_t)batch * h * w;
+  dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (cout + CG_BN - 1) / CG_BN);
+  conv_gemm_ffma_kernel<9><<<grid, 256, 0, as_stream(stream)>>>(a);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, const float* s,
+                                        const float* d, const float* noise,
+                                        int64_t noise_batch_stride, const float* noise_w,
+                                        const float* act_bias, float* y, int batch, int h, int w,
+                                        int cin, int cout, void* scratch, size_t scratch_bytes,
+                                        void* stream) {
+  int rc = check_conv_shapes("e3_styled_conv3x3_up_fwd", batch, h, w, cin, cout);
+  if (rc) return rc;
+  if (batch == 0) return E3_OK;
+  E3_REQUIRE(x && wpacked && s && d && y, E3_ERR_BAD_ARG, "e3_styled_conv3x3_up_fwd: null argument");
+  E3_REQUIRE(!act_bias || (noise && noise_w), E3_ERR_BAD_ARG,
+             "e3_styled_conv3x3_up_fwd: noise and noise_w are required unless act_bias is NULL");
+  const size_t need = e3_styled_conv_scratch_bytes(batch, h, w, cin, cout, 1);
+  E3_REQUIRE(scratch && scratch_bytes >= need, E3_ERR_SCRATCH,
+             "e3_styled_conv3x3_up_fwd: scratch %zu < %zu bytes", scratch_bytes, need);
+  ConvGemmArgs a{};
+  a.x = x, a.s = s, a.wg = static_cast<const float*>(wpacked), a.out = static_cast<float*>(scratch);
+  a.B = batch, a.H = h, a.W = w, a.Cin = cin, a.N = 9 * cout;
+  a.mode = 0;
+  const int64_t M = (int64_t)batch * h * w;
+  dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (a.N + CG_BN - 1) / CG_BN);
+  conv_gemm_ffma_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a);
+  E3_CUDA(cudaGetLastError());
+  Col2imArgs c{};
+  c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
+  c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;
+  c.act_bias = act_bias;
+  const int64_t total = (int64_t)batch * 4 * h * w * (cout / 4);
+  col2im_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(c);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" int e3_torgb_fwd(const float* x, const float* weight, const float* s, const float* bias,
+                            const float* skip, int upsample_skip, float* rgb, int batch, int h, int w,
+                            int cin, void* stream) {
+  E3_REQUIRE(batch >= 0 && h > 0 && w > 0 && cin > 0 && cin % 4 == 0 && batch <= 65535,
+             E3_ERR_BAD_ARG, "e3_torgb_fwd: bad shape (cin %% 4 == 0 required)");
+  E3_REQUIRE(!(skip && upsample_skip) || (h % 2 == 0 && w % 2 == 0), E3_ERR_BAD_ARG,
+             "e3_torgb_fwd: upsampled skip needs even output size");
+  if (batch == 0) return E3_OK;
+  E3_REQUIRE(x && weight && s && bias && rgb, E3_ERR_BAD_ARG, "e3_torgb_fwd: null argument");
+  ToRgbArgs a{x, weight, s, bias, skip, upsample_skip, rgb, batch, h, w, cin};
+  int bx = (h * w + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (bx > cap) bx = cap;
+  torgb_kernel<<<dim3(bx, batch), 256, 3 * cin * sizeof(float), as_stream(stream)>>>(a);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" int e3_pack_inversion_record(const float* w_plus, const float* w_dec, int n_latent,
+                                        const float* image, const float* target, int batch,
+                                        int64_t image_numel, float* record, void* stream) {
+  E3_REQUIRE(w_plus && w_dec && record && n_latent > 0 && batch >= 0, E3_ERR_BAD_ARG,
+             "e3_pack_inversion_record: bad argument");
+  E3_REQUIRE((image == nullptr) == (target == nullptr), E3_ERR_BAD_ARG,
+             "e3_pack_inversion_record: image and target come together");
+  if (batch == 0) return E3_OK;
+  pack_record_kernel<<<batch, 256, 0, as_stream(stream)>>>(w_plus, w_dec, n_latent, image, target,
+                                                          image_numel > 0 ? image_numel : 1, record);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}

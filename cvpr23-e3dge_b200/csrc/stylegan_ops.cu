@@ -1,0 +1,192 @@
+// sm_100a rewrites of the reference's two CUDA extensions, same semantics and argument
+// order as its pybind ABI:
+//   fused.fused_bias_act   project/models/op/fused_bias_act.cpp:11-20,
+//                          fused_bias_act_kernel.cu:19-99
+//   upfirdn2d_op.upfirdn2d project/models/op/upfirdn2d.cpp:12-23, upfirdn2d_kernel.cu:49-310
+// Both are pure HBM streams: algorithmic bytes = (numel_in + numel_out) * 4.
+#include "common.cuh"
+
+namespace e3 {
+
+// y = act(x + b[(i / step_b) % size_b]) * scale, grad variants gated by the saved output.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) fused_bias_act_kernel(
+    const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ refer,
+    float* __restrict__ y, int64_t numel, int64_t step_b, int64_t size_b, int mode, float alpha,
+    float scale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto apply = [&](float v, float r) -> float {
+    float o;
+    switch (mode) {
+      case 12:
+      case 32: o = 0.f; break;
+      case 30: o = (v > 0.f) ? v : v * alpha; break;
+      case 31: o = (r > 0.f) ? v : v * alpha; break;
+      default: o = v; break;  // 10, 11: linear
+    }
+    return o * scale;
+  };
+  if (VEC4) {
+    // step_b % 4 == 0: the 4 lanes of a vector share one bias element
+    const int64_t n4 = numel >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      float4 r = refer ? reinterpret_cast<const float4*>(refer)[i] : make_float4(0, 0, 0, 0);
+      const float b = bias ? bias[((i << 2) / step_b) % size_b] : 0.f;
+      float4 o;
+      o.x = apply(v.x + b, r.x), o.y = apply(v.y + b, r.y), o.z = apply(v.z + b, r.z),
+      o.w = apply(v.w + b, r.w);
+      reinterpret_cast<float4*>(y)[i] = o;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+      const float b = bias ? bias[(i / step_b) % size_b] : 0.f;
+      y[i] = apply(x[i] + b, refer ? refer[i] : 0.f);
+    }
+  }
+}
+
+struct UpfirdnArgs {
+  int major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, out_h, out_w;
+};
+
+// out[oy,ox] = sum_{ky,kx} U[oy*down + ky - pad0] * k[kh-1-ky][kw-1-kx]; U = zero-inserted input.
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict__ x,
+                                                        const float* __restrict__ kernel,
+                                                        float* __restrict__ y, UpfirdnArgs a) {
+  __shared__ float sk[256];
+  const int ktaps = a.kh * a.kw;
+  const bool k_in_smem = ktaps <= 256;
+  if (k_in_smem) {
+    for (int i = threadIdx.x; i < ktaps; i += blockDim.x) sk[i] = kernel[i];
+    __syncthreads();
+  }
+  const float* kp = k_in_smem ? sk : kernel;
+  const int64_t total = (int64_t)a.major * a.out_h * a.out_w * a.minor;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int mi = (int)(idx % a.minor);
+    int64_t t = idx / a.minor;
+    const int ox = (int)(t % a.out_w);
+    t /= a.out_w;
+    const int oy = (int)(t % a.out_h);
+    const int mj = (int)(t / a.out_h);
+    const int base_y = oy * a.down_y - a.pad_y0, base_x = ox * a.down_x - a.pad_x0;
+    const float* xp = x + (int64_t)mj * a.in_h * a.in_w * a.minor + mi;
+    float acc = 0.f;
+    for (int ky = 0; ky < a.kh; ++ky) {
+      const int uy = base_y + ky;
+      if (uy < 0 || uy % a.up_y) continue;
+      const int iy = uy / a.up_y;
+      if (iy >= a.in_h) continue;
+      for (int kx = 0; kx < a.kw; ++kx) {
+        const int ux = base_x + kx;
+        if (ux < 0 || ux % a.up_x) continue;
+        const int ix = ux / a.up_x;
+        if (ix >= a.in_w) continue;
+        acc = fmaf(xp[((int64_t)iy * a.in_w + ix) * a.minor],
+                   kp[(a.kh - 1 - ky) * a.kw + (a.kw - 1 - kx)], acc);
+      }
+    }
+    y[idx] = acc;
+  }
+}
+
+// NCHW <-> NHWC through a 32x32 shared-memory transpose (planes: [C][HW] <-> [HW][C]).
+__global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __restrict__ x,
+                                                               float* __restrict__ y, int rows,
+                                                               int cols) {
+  // x: [batch][rows][cols] -> y: [batch][cols][rows]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* xb = x + (size_t)b * rows * cols;
+  float* yb = y + (size_t)b * rows * cols;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = xb[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) yb[(size_t)c * rows + r] = tile[tx][i];
+  }
+}
+
+static int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace e3
+
+using namespace e3;
+
+extern "C" int e3_fused_bias_act(const float* x, const float* bias, const float* refer, float* y,
+                                 int64_t numel, int64_t step_b, int64_t size_b, int act, int grad,
+                                 float alpha, float scale, void* stream) {
+  E3_REQUIRE(numel >= 0, E3_ERR_BAD_ARG, "e3_fused_bias_act: negative numel");
+  if (numel == 0) return E3_OK;
+  E3_REQUIRE(x && y, E3_ERR_BAD_ARG, "e3_fused_bias_act: null tensor");
+  E3_REQUIRE((act == 1 || act == 3) && grad >= 0 && grad <= 2, E3_ERR_BAD_ARG,
+             "e3_fused_bias_act: act=%d grad=%d not supported (act in {1,3}, grad in {0,1,2})", act,
+             grad);
+  E3_REQUIRE(!bias || (step_b > 0 && size_b > 0), E3_ERR_BAD_ARG,
+             "e3_fused_bias_act: bias needs step_b, size_b > 0");
+  const int mode = act * 10 + grad;
+  const bool vec = (numel % 4 == 0) && (!bias || step_b % 4 == 0) &&
+                   (((uintptr_t)x | (uintptr_t)y | (uintptr_t)refer) % 16 == 0);
+  if (vec)
+    fused_bias_act_kernel<true><<<grid_for(numel / 4, 256), 256, 0, as_stream(stream)>>>(
+        x, bias, refer, y, numel, step_b, size_b, mode, alpha, scale);
+  else
+    fused_bias_act_kernel<false><<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>(
+        x, bias, refer, y, numel, step_b, size_b, mode, alpha, scale);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" int e3_upfirdn2d(const float* x, const float* kernel, float* y, int major, int in_h,
+                            int in_w, int minor, int kh, int kw, int up_x, int up_y, int down_x,
+                            int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                            void* stream) {
+  E3_REQUIRE(major >= 0 && in_h > 0 && in_w > 0 && minor > 0 && kh > 0 && kw > 0, E3_ERR_BAD_ARG,
+             "e3_upfirdn2d: bad shape");
+  E3_REQUIRE(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0, E3_ERR_BAD_ARG,
+             "e3_upfirdn2d: up/down factors must be positive");
+  UpfirdnArgs a{major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, 0, 0};
+  a.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+  a.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+  E3_REQUIRE(a.out_h > 0 && a.out_w > 0, E3_ERR_BAD_ARG, "e3_upfirdn2d: empty output %dx%d",
+             a.out_h, a.out_w);
+  if (major == 0) return E3_OK;
+  E3_REQUIRE(x && kernel && y, E3_ERR_BAD_ARG, "e3_upfirdn2d: null tensor");
+  const int64_t total = (int64_t)major * a.out_h * a.out_w * minor;
+  upfirdn2d_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, kernel, y, a);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+static int transpose_planes(const float* x, float* y, int batch, int rows, int cols, void* stream) {
+  E3_REQUIRE(batch >= 0 && rows > 0 && cols > 0, E3_ERR_BAD_ARG, "layout conversion: bad shape");
+  if (batch == 0) return E3_OK;
+  E3_REQUIRE(x && y, E3_ERR_BAD_ARG, "layout conversion: null tensor");
+  E3_REQUIRE(batch <= 65535, E3_ERR_UNSUPPORTED, "layout conversion: batch > 65535");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+  transpose_planes_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, rows, cols);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" int e3_nchw_to_nhwc(const float* x, float* y, int batch, int ch, int h, int w,
+                               void* stream) {
+  return transpose_planes(x, y, batch, ch, h * w, stream);
+}
+extern "C" int e3_nhwc_to_nchw(const float* x, float* y, int batch, int ch, int h, int w,
+                               void* stream) {
+  return transpose_planes(x, y, batch, h * w, ch, stream);
+}

@@ -1,0 +1,144 @@
+"""ctypes binding of the C-ABI library (include/e3dge_b200.h).
+
+The library is built in-tree by ``cvpr23-e3dge_b200/build.py``.  There is no fallback of
+any kind: if the shared object is missing, loading raises, and every op raises on
+non-CUDA tensors.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_uint32, c_void_p)
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libe3dge_b200.so")
+
+_fp = c_void_p  # every device pointer crosses the ABI as void*
+
+
+class SirenWeights(Structure):
+    _fields_ = [("pts_w", _fp * 8), ("pts_b", _fp * 8), ("gamma_w", _fp * 9), ("gamma_b", _fp * 9),
+                ("beta_w", _fp * 9), ("beta_b", _fp * 9), ("views_w", _fp), ("views_b", _fp),
+                ("rgb_w", _fp), ("rgb_b", _fp), ("sigma_w", _fp), ("sigma_b", _fp)]
+
+
+class RenderParams(Structure):
+    _fields_ = [("batch", c_int32), ("height", c_int32), ("width", c_int32), ("res", c_int32),
+                ("n_samples", c_int32), ("flags", c_uint32), ("pts_scale", c_float),
+                ("mask_depth", c_float)]
+
+
+class RenderInputs(Structure):
+    _fields_ = [(n, _fp) for n in ("cam_poses", "focal", "near", "far", "pix_x", "pix_y", "t_vals",
+                                   "z_jitter", "sigmoid_beta", "film", "local_alpha", "local_beta")]
+
+
+class RenderOutputs(Structure):
+    _fields_ = [(n, _fp) for n in ("features", "thumb_rgb", "xyz", "mask", "depth", "sdf", "hit_prob",
+                                   "visibility", "dists", "points", "rays_o", "rays_d", "viewdirs",
+                                   "raw_rgb", "feats_taps")]
+
+
+RENDER_STATIC_VIEWDIRS = 1
+RENDER_FORCE_BACKGROUND = 2
+RENDER_NO_FORCE_STOP = 4
+RENDER_NO_SDF = 8
+
+_PROTOTYPES = {
+    "e3_abi_version": (c_int, []),
+    "e3_last_error": (c_char_p, []),
+    "e3_siren_packed_bytes": (c_size_t, []),
+    "e3_siren_pack": (c_int, [POINTER(SirenWeights), _fp, _fp]),
+    "e3_film_fwd": (c_int, [_fp, _fp, c_int, c_int, _fp, _fp]),
+    "e3_render_fwd": (c_int, [_fp, POINTER(RenderParams), POINTER(RenderInputs),
+                              POINTER(RenderOutputs), _fp]),
+    "e3_siren_points_fwd": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, _fp]),
+    "e3_fused_bias_act": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_int64, c_int64, c_int, c_int,
+                                  c_float, c_float, _fp]),
+    "e3_upfirdn2d": (c_int, [_fp, _fp, _fp] + [c_int] * 14 + [_fp]),
+    "e3_modconv_weight_sq": (c_int, [_fp, c_int, c_int, c_int, _fp, _fp]),
+    "e3_modconv_styles": (c_int, [_fp, c_int64, _fp, _fp, _fp, c_int, c_int, c_int, c_int, _fp, _fp,
+                                  _fp]),
+    "e3_nchw_to_nhwc": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp]),
+    "e3_nhwc_to_nchw": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp]),
+    "e3_conv_packed_bytes": (c_size_t, [c_int, c_int]),
+    "e3_conv_pack_weight": (c_int, [_fp, c_int, c_int, c_int, _fp, _fp]),
+    "e3_styled_conv3x3_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, c_int, c_int,
+                                      c_int, c_int, c_int, _fp, c_size_t, _fp]),
+    "e3_styled_conv3x3_up_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, c_int,
+                                         c_int, c_int, c_int, c_int, _fp, c_size_t, _fp]),
+    "e3_styled_conv_scratch_bytes": (c_size_t, [c_int] * 6),
+    "e3_torgb_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, _fp, c_int, c_int, c_int, c_int, _fp]),
+    "e3_pack_inversion_record": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int64, _fp, _fp]),
+    "e3_ffma_peak_probe": (c_int, [c_int, _fp, _fp]),
+    "e3_ffma_peak_probe_sink_floats": (c_size_t, []),
+}
+
+_lib = None
+
+
+def load():
+    """Loads (once) and returns the ctypes handle.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"e3dge_b200: native library not found at {LIB_PATH}. Build it with "
+            "`python cvpr23-e3dge_b200/build.py` (or __graft_entry__.build()); there is no "
+            "non-CUDA fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+# kernels launched by one successful call of each entry point (for bench.py's gpu_launches)
+KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
+                    "e3_siren_points_fwd": 1, "e3_fused_bias_act": 1, "e3_upfirdn2d": 1,
+                    "e3_modconv_weight_sq": 1, "e3_modconv_styles": 2, "e3_nchw_to_nhwc": 1,
+                    "e3_nhwc_to_nchw": 1, "e3_conv_pack_weight": 1, "e3_styled_conv3x3_fwd": 1,
+                    "e3_styled_conv3x3_up_fwd": 2, "e3_torgb_fwd": 1,
+                    "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1}
+launch_count = 0
+
+
+def check(rc, what="", launches=None):
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(what, 0) if launches is None else launches
+    if rc != 0:
+        msg = load().e3_last_error()
+        raise RuntimeError(f"e3dge_b200 {what} failed (status {rc}): "
+                           f"{msg.decode() if msg else 'no message'}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("e3dge_b200: CUDA tensor required (this framework has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"e3dge_b200: float32 tensor required, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("e3dge_b200: contiguous tensor required")
+    return c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def as_f32c(t):
+    """fp32 contiguous view/copy (the reference makes inputs .contiguous() inside the op)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,251 @@
+/*
+ * e3dge_b200 — C ABI of the B200-native StyleSDF generator hot path for E3DGE.
+ *
+ * Drop-in boundary.  The reference has no C ABI of its own: its two
+ * pybind shims (project/models/op/fused_bias_act.cpp:11-20, upfirdn2d.cpp:12-23) and the
+ * Python surfaces of project/utils/volume_renderer.py / project/models/stylesdf_model.py
+ * are what a maintainer binds to.  Every entry point below names the reference interface
+ * it replaces.
+ *
+ * Conventions (derived from the reference's shims, SURVEY.md §8b "Conventions"):
+ *   - all pointers are DEVICE pointers to caller-owned, contiguous buffers unless the
+ *     name ends in `_host`; the library never allocates or frees caller-visible memory;
+ *     scratch is passed in by the caller (sizes from the *_bytes() queries);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host sync;
+ *   - return value: 0 ok; E3_ERR_* (<0) bad argument; >0 a cudaError_t passthrough;
+ *     e3_last_error() gives a thread-local human-readable message;
+ *   - re-entrant, no global mutable state; optional outputs may be NULL (= not wanted);
+ *   - fp32 in / fp32 out (the reference never runs AMP, SURVEY.md §8b "Dtypes").
+ */
+#ifndef E3DGE_B200_H_
+#define E3DGE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E3_OK 0
+#define E3_ERR_BAD_ARG (-1)
+#define E3_ERR_UNSUPPORTED (-2)
+#define E3_ERR_SCRATCH (-3)
+
+#define E3_SIREN_WIDTH 256 /* rendering.width, options.py (FiLM-SIREN hidden size) */
+#define E3_SIREN_DEPTH 8   /* rendering.depth */
+#define E3_STYLE_DIM 256   /* model.style_dim */
+
+int e3_abi_version(void);
+const char* e3_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * FiLM-SIREN weights (SirenGenerator, volume_renderer.py:136-166) in reference layout.
+ * state_dict names: renderer.network[.netGlobal].{pts_linears.i,views_linears}.{weight,
+ * bias,gamma.weight,gamma.bias,beta.weight,beta.bias}, rgb_linear.*, sigma_linear.*
+ * ---------------------------------------------------------------------------------- */
+typedef struct e3_siren_weights {
+  const float* pts_w[8];   /* [256,3] for i=0, [256,256] otherwise (out,in) row-major */
+  const float* pts_b[8];   /* [256] */
+  const float* gamma_w[9]; /* [256,256]; index 8 = views_linears */
+  const float* gamma_b[9]; /* [256] */
+  const float* beta_w[9];  /* [256,256] */
+  const float* beta_b[9];  /* [256] */
+  const float* views_w;    /* [256,259] */
+  const float* views_b;    /* [256] */
+  const float* rgb_w;      /* [3,256] */
+  const float* rgb_b;      /* [3] */
+  const float* sigma_w;    /* [1,256] */
+  const float* sigma_b;    /* [1] */
+} e3_siren_weights;
+
+/* Bytes of the library-private packed weight image (TMA-friendly k-major slabs). */
+size_t e3_siren_packed_bytes(void);
+/* Repack once per weight update (frozen generator => once).  `packed` must be 128-byte
+ * aligned and e3_siren_packed_bytes() large. */
+int e3_siren_pack(const e3_siren_weights* w, void* packed, void* stream);
+
+/* FiLM frequencies/phases for a batch:  gamma = 15*(G w + g) + 30, beta = 0.25*(H w + h)
+ * (FiLMSiren.gamma/.beta, volume_renderer.py:107-114,119-120).
+ * styles [batch, styles_per_image, 256]; styles_per_image is 9 (w+: layer i uses style i,
+ * the view layer uses the last one, volume_renderer.py:176-178,226-227) or 1 (w).
+ * film [batch, 9, 2, 256] (gamma row then beta row per layer). */
+int e3_film_fwd(const void* packed, const float* styles, int batch, int styles_per_image,
+                float* film, void* stream);
+
+/* flags of e3_render_params */
+#define E3_RENDER_STATIC_VIEWDIRS 1u  /* rendering.static_viewdirs (volume_renderer.py:789-792) */
+#define E3_RENDER_FORCE_BACKGROUND 2u /* rendering.force_background (:884-886) */
+#define E3_RENDER_NO_FORCE_STOP 4u    /* volume_integration(no_force_stop=True) (:830-836) */
+#define E3_RENDER_NO_SDF 8u           /* rendering.no_sdf: softplus density (:862-867) */
+
+typedef struct e3_render_params {
+  int32_t batch;
+  int32_t height;    /* rays per column  = out_im_res * spatial_ss */
+  int32_t width;     /* rays per row */
+  int32_t res;       /* out_im_res: principal point = res/2 (volume_renderer.py:773-774) */
+  int32_t n_samples; /* rendering.N_samples, <= 96 */
+  uint32_t flags;
+  float pts_scale;   /* 1/dist_radius, UniformBoxWarp (:23-30,720) */
+  float mask_depth;  /* 1.08 (:910) */
+} e3_render_params;
+
+/* Inputs of one render call (VolumeFeatureRenderer.forward, volume_renderer.py:1865). */
+typedef struct e3_render_inputs {
+  const float* cam_poses;    /* [B,3,4] camera-to-world */
+  const float* focal;        /* [B] */
+  const float* near;         /* [B] */
+  const float* far;          /* [B] */
+  const float* pix_x;        /* [width]  pixel centres, the `i` buffer (:666-674) */
+  const float* pix_y;        /* [height] pixel centres, the `j` buffer */
+  const float* t_vals;       /* [n_samples] the `t_vals` buffer (:690-698) */
+  const float* z_jitter;     /* NULL, or [B,H,W,S] replacement z_vals (perturb > 0, :1213-1228) */
+  const float* sigmoid_beta; /* [1] learned (:662-663) */
+  const float* film;         /* [B,9,2,256] from e3_film_fwd */
+  const float* local_alpha;  /* NULL or [B,H,W,S,256]: (alpha+1)*h + beta before the view */
+  const float* local_beta;   /*                        layer (:217-220) */
+} e3_render_inputs;
+
+/* Outputs: the dict contract of render_rays / forward (volume_renderer.py:1270-1287,
+ * 1957-1968).  Any pointer may be NULL. */
+typedef struct e3_render_outputs {
+  float* features;   /* [B,256,H,W] */
+  float* thumb_rgb;  /* [B,3,H,W]   'gen_thumb_imgs' */
+  float* xyz;        /* [B,3,H,W] */
+  float* mask;       /* [B,1,H,W,1] */
+  float* depth;      /* [B,H,W,1,1] */
+  float* sdf;        /* [B,H,W,S,1] */
+  float* hit_prob;   /* [B,H,W,S,1] 'hit_prob' = weights */
+  float* visibility; /* [B,H,W,S,1] transmittance T_s */
+  float* dists;      /* [B,H,W,S] */
+  float* points;     /* [B,H,W,S,3] world-space samples */
+  float* rays_o;     /* [B,H,W,3] */
+  float* rays_d;     /* [B,H,W,3] */
+  float* viewdirs;   /* [B,H,W,3] normalised */
+  float* raw_rgb;    /* [B,H,W,S,3] pre-sigmoid radiance (run_network(...)[..., :3]) */
+  float* feats_taps; /* NULL or [4,B,H,W,S,256]: hidden states after layers 1,3,5,7
+                        (rendering.return_feats, volume_renderer.py:172-193) */
+} e3_render_outputs;
+
+/* Fused rays -> samples -> FiLM-SIREN x9 -> SDF->sigma -> alpha composite.
+ * Replaces VolumeFeatureRenderer.render/render_rays/run_network/volume_integration
+ * (volume_renderer.py:1666-1701, 1183-1298, 1052-1128, 809-943) and
+ * SirenGenerator.forward (:240-264) for the inference wiring. */
+int e3_render_fwd(const void* packed, const e3_render_params* p, const e3_render_inputs* in,
+                  const e3_render_outputs* out, void* stream);
+
+/* FiLM-SIREN evaluated at arbitrary world-space points (run_network on explicit samples:
+ * volume_renderer.py:955-957, 996-998, 1935-1943).
+ * points [B,N,3]; viewdirs NULL (= zeros, geometry queries) or [B,N,3];
+ * sdf [B,N]; raw_rgb NULL or [B,N,3]; feat NULL or [B,N,256].  When raw_rgb and feat are
+ * both NULL the view layer is skipped (return_sdf_only, :1125-1126). */
+int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
+                        const float* viewdirs, int batch, int n_points, float pts_scale,
+                        float* sdf, float* raw_rgb, float* feat, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * StyleGAN2 ops — same semantics and argument order as the reference's extension ABI.
+ * ---------------------------------------------------------------------------------- */
+
+/* fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ * (fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:19-99).  x/y have `numel` elements;
+ * bias (may be NULL) has `size_b` elements and applies along dim 1 with `step_b` =
+ * prod(dims[2:]); refer (may be NULL) is the saved output for grad=1.  act: 1 linear,
+ * 3 leaky-ReLU; grad: 0,1,2. */
+int e3_fused_bias_act(const float* x, const float* bias, const float* refer, float* y,
+                      int64_t numel, int64_t step_b, int64_t size_b, int act, int grad,
+                      float alpha, float scale, void* stream);
+
+/* upfirdn2d_op.upfirdn2d(input[major,in_h,in_w,minor], kernel[kh,kw], up_x, up_y, down_x,
+ * down_y, pad_x0, pad_x1, pad_y0, pad_y1) (upfirdn2d.cpp:12-23, upfirdn2d_kernel.cu).
+ * y is [major,out_h,out_w,minor] with out = (in*up + pad0 + pad1 - k)/down + 1. */
+int e3_upfirdn2d(const float* x, const float* kernel, float* y, int major, int in_h,
+                 int in_w, int minor, int kh, int kw, int up_x, int up_y, int down_x,
+                 int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Modulated-conv decoder (Decoder / StyledConv / ToRGB, stylesdf_model.py:263-362,
+ * 469-541, 587-797).
+ * ---------------------------------------------------------------------------------- */
+
+/* Per-sample modulation and demodulation factors of one ModulatedConv2d
+ * (stylesdf_model.py:319-326):
+ *   s[b,i]  = (mod_w[i,:]/sqrt(512)) . latent[b,:] + mod_b[i]
+ *   d[b,o]  = rsqrt( sum_{i,k} (W[o,i,k]/sqrt(cin*k*k) * s[b,i])^2 + 1e-8 )   (d may be NULL)
+ * latent rows are `latent_stride` floats apart (latent[:, layer] views of [B,n_latent,512]).
+ * wsq [cout,cin] = sum_k W[o,i,k]^2, from e3_modconv_weight_sq. */
+int e3_modconv_weight_sq(const float* weight, int cout, int cin, int ksize, float* wsq,
+                         void* stream);
+int e3_modconv_styles(const float* latent, int64_t latent_stride, const float* mod_w,
+                      const float* mod_b, const float* wsq, int batch, int cin, int cout,
+                      int ksize, float* s, float* d, void* stream);
+
+/* Activations inside the decoder are channels-last (NHWC) fp32.
+ * e3_nchw_to_nhwc / e3_nhwc_to_nchw convert at the boundary. */
+int e3_nchw_to_nhwc(const float* x, float* y, int batch, int ch, int h, int w, void* stream);
+int e3_nhwc_to_nchw(const float* x, float* y, int batch, int ch, int h, int w, void* stream);
+
+/* Library-private packed image of one 3x3 conv weight [cout,cin,3,3] (reference layout,
+ * `decoder.*.conv.weight` without its leading 1): the equalised-lr scale 1/sqrt(cin*9)
+ * (stylesdf_model.py:301-302) is folded in and the taps are laid out GEMM-major
+ * (plain: [tap][cin][cout]; upsample: [cin][tap*cout]).  Pack once per weight update. */
+size_t e3_conv_packed_bytes(int cout, int cin);
+int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample, void* packed,
+                        void* stream);
+
+/* StyledConv forward, plain 3x3 (stylesdf_model.py:356-360, 494-507):
+ *   y = lrelu_0.2( d[b,o] * conv3x3(x * s[b,:], W/sqrt(cin*9)) + noise_w*noise[y,x]
+ *                  + act_bias[o] ) * sqrt(2)
+ * x [B,H,W,cin] NHWC, wpacked from e3_conv_pack_weight(upsample=0), noise [H,W] (the
+ * registered noise_k buffer or a caller tensor; per-sample noise: noise_batch_stride=H*W,
+ * else 0), y [B,H,W,cout] NHWC.  cin % 16 == 0, cout % 4 == 0.
+ * act_bias == NULL selects the bare ModulatedConv2d.forward (y = d * conv(x*s, W), no noise,
+ * bias or activation; stylesdf_model.py:317-362); noise / noise_w may then be NULL too. */
+int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const float* s, const float* d,
+                          const float* noise, int64_t noise_batch_stride,
+                          const float* noise_w, const float* act_bias, float* y, int batch,
+                          int h, int w, int cin, int cout, void* scratch,
+                          size_t scratch_bytes, void* stream);
+
+/* StyledConv forward, upsampling (stylesdf_model.py:331-346, 283-291): conv_transpose2d
+ * stride 2 followed by the 4x4 [1,3,3,1] blur (gain 4, pad (1,1)), then noise + bias +
+ * leaky-ReLU as above.  x [B,H,W,cin] -> y [B,2H,2W,cout]; noise [2H,2W];
+ * wpacked from e3_conv_pack_weight(upsample=1). */
+int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, const float* s,
+                             const float* d, const float* noise,
+                             int64_t noise_batch_stride, const float* noise_w,
+                             const float* act_bias, float* y, int batch, int h, int w,
+                             int cin, int cout, void* scratch, size_t scratch_bytes,
+                             void* stream);
+size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout, int upsample);
+
+/* ToRGB forward (stylesdf_model.py:531-541, Upsample :96-119): 1x1 modulated conv without
+ * demodulation + bias + (optionally FIR-upsampled) skip.
+ * x [B,H,W,cin] NHWC; weight [3,cin]; skip NULL, or [B,3,H/2,W/2] NCHW when
+ * upsample_skip != 0 (upfirdn2d up=2, kernel [1,3,3,1]^2/64*4, pad (2,1)), or [B,3,H,W];
+ * rgb [B,3,H,W] NCHW (the image contract of the reference). */
+int e3_torgb_fwd(const float* x, const float* weight, const float* s, const float* bias,
+                 const float* skip, int upsample_skip, float* rgb, int batch, int h, int w,
+                 int cin, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Image-parallel inversion record: packs, per image, the renderer latent
+ * w+ [9*256], the decoder latent [n_latent*512] and K metric scalars into one contiguous
+ * fp32 row of the all-gather send buffer, computing the metrics (mean squared error and
+ * mean absolute error of `image` vs `target`, both [B,3,H,W]) on the device.
+ * record [B, 2304 + n_latent*512 + 2]. */
+int e3_pack_inversion_record(const float* w_plus, const float* w_dec, int n_latent,
+                             const float* image, const float* target, int batch,
+                             int64_t image_numel, float* record, void* stream);
+
+/* Measurement aid (bench.py roofline denominator): runs `iters` rounds of 16 independent
+ * FFMA chains per thread on every SM and writes one float per thread to `sink`
+ * (sm_count*1024 floats... see e3_ffma_peak_probe_sink_floats).  FLOPs performed =
+ * sink_floats * iters * 16 * 2. */
+int e3_ffma_peak_probe(int iters, float* sink, void* stream);
+size_t e3_ffma_peak_probe_sink_floats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E3DGE_B200_H_ */

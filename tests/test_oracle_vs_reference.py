@@ -1,0 +1,54 @@
+"""Live pin of the oracle and of the state_dict contract against the REAL reference.
+Only runs where /root/reference exists (the build container); runs the reference in a
+subprocess because its top-level package is called `project`, like our shim."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+from oracle import ref_harness as rh
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
+
+_SCRIPT = r"""
+import json, sys, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests')
+from oracle import ref_harness as rh, params as P, stylesdf_oracle as O
+from helpers import generator_state_dict_spec, rel_linf
+ref = rh.load_reference()
+res = {}
+for size, r, local in ((256, 64, False), (1024, 64, False)):
+    G = ref.stylesdf_model.G_pred_latents(rh.model_opt(size=size, renderer_spatial_output_dim=r),
+                                          rh.rendering_opt())
+    got = {k: tuple(v.shape) for k, v in G.state_dict().items()}
+    want = {k: tuple(v) for k, v in generator_state_dict_spec(size, r, local).items()}
+    res['keys_%%d' %% size] = (got == want)
+# live forward: reference vs oracle, random-init weights of the reference itself
+torch.manual_seed(3)
+G = ref.stylesdf_model.G_pred_latents(rh.model_opt(size=64, renderer_spatial_output_dim=16),
+                                      rh.rendering_opt()).eval()
+sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+inp = P.make_inputs(5, 2, G.decoder.n_latent, 16)
+with torch.no_grad():
+    a = G([inp['w'], inp['w_dec']], inp['cam_poses'], inp['focal'], inp['near'], inp['far'],
+          input_is_latent=True, randomize_noise=False, return_xyz=True, return_sdf=True)
+    b = O.generator_forward(sd, inp['w'], inp['w_dec'], inp['cam_poses'], inp['focal'],
+                            inp['near'], inp['far'], res=16, n_samples=24)
+res['err'] = {k: rel_linf(b[k], a[k]) for k in ('features', 'gen_thumb_imgs', 'sdf', 'hit_prob',
+                                                 'xyz', 'depth', 'dists', 'points', 'gen_imgs')}
+print('RESULT ' + json.dumps(res))
+"""
+
+
+def test_oracle_and_contract_against_live_reference():
+    r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": ROOT}], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    res = json.loads(line[7:])
+    assert res["keys_256"] and res["keys_1024"]
+    for k, e in res["err"].items():
+        assert e < 2e-5, (k, e)
