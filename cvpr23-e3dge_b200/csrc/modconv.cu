@@ -14,9 +14,12 @@
 // at its minimum FLOP count: a 1x1-style GEMM  G[pix, (ky,kx,o)] = sum_i xs[pix,i] *
 // W[o,i,ky,kx]  followed by a fused col2im + blur + noise + bias + leaky-ReLU gather.
 //
-// This file is the fp32 CUDA-core (FFMA) implementation: exact-fp32 arithmetic, used for
-// parity and as the numerical baseline of the tcgen05 path.
-#include "common.cuh"
+// Two arithmetic back ends behind the same entry points (flags E3_CONV_*):
+//   * tensor cores (tc_conv.cu): tcgen05 split-bf16 implicit GEMM, TMA-fed — the fast path for
+//     the decoder's real shapes (power-of-two maps, Cin % 64 == 0, N % 128 == 0);
+//   * CUDA cores (this file): exact-fp32 FFMA implicit GEMM for every other shape, and the
+//     numerical baseline the tensor-core path is tested against.
+#include "modconv.cuh"
 
 namespace e3 {
 
@@ -90,21 +93,6 @@ __global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ ws
 // ---- implicit-GEMM conv on the FFMA pipe ---------------------------------------------------
 // C[m][n] = sum_{tap,ci} (x[b, y+dy, x+dx, ci] * s[b,ci]) * Wg[tap][ci][n],  m = (b,y,x)
 // 128x128 tile, BK = 16, 256 threads, 8x8 register tile, register-staged double buffering.
-struct ConvGemmArgs {
-  const float* x;   // [B,H,W,Cin]
-  const float* s;   // [B,Cin]
-  const float* wg;  // [TAPS][Cin][N]
-  float* out;       // [M][N]
-  int B, H, W, Cin, N;
-  // epilogue: mode 0 raw store; 1 lrelu(d*acc + noise_w*noise + bias)*sqrt2; 2 d*acc
-  int mode;
-  const float* d;         // [B,N]
-  const float* noise;     // [H*W] (+ b*noise_bstride)
-  int64_t noise_bstride;
-  const float* noise_w;   // [1]
-  const float* act_bias;  // [N]
-};
-
 constexpr int CG_BM = 128, CG_BN = 128, CG_BK = 16, CG_LDA = CG_BM + 4;
 
 template <int TAPS>
@@ -446,8 +434,12 @@ extern "C" int e3_modconv_styles(const float* latent, int64_t latent_stride, con
   return E3_OK;
 }
 
+// packed image: [fp32 GEMM-major (cout*cin*9 floats)] [bf16 hi K-major] [bf16 lo K-major]
 extern "C" size_t e3_conv_packed_bytes(int cout, int cin) {
-  return (size_t)cout * cin * 9 * sizeof(float);
+  return (size_t)cout * cin * 9 * (sizeof(float) + 2 * 2);
+}
+static inline const void* packed_bf16_part(const void* packed, int cout, int cin) {
+  return static_cast<const char*>(packed) + (size_t)cout * cin * 9 * sizeof(float);
 }
 
 extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample,
@@ -457,13 +449,20 @@ extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int u
   conv_pack_kernel<<<grid_cap(((int64_t)cout * cin * 9 + 255) / 256), 256, 0, as_stream(stream)>>>(
       weight, cout, cin, upsample, scale, static_cast<float*>(packed));
   E3_CUDA(cudaGetLastError());
-  return E3_OK;
+  return tc_conv_pack_weight(weight, cout, cin, upsample, scale,
+                             const_cast<void*>(packed_bf16_part(packed, cout, cin)), as_stream(stream));
 }
 
+static bool use_tensor_cores(uint32_t flags, int batch, int h, int w, int cin, int n) {
+  if (flags & E3_CONV_FP32_CUDA_CORES) return false;
+  return tc_conv_supported(batch, h, w, cin, n);
+}
+
+// scratch = [G (upsample only): B*H*W*9*cout fp32] [xs_hi | xs_lo: B*H*W*cin bf16 each]
 extern "C" size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout,
                                                int upsample) {
-  (void)cin;
-  return upsample ? (size_t)batch * h * w * 9 * cout * sizeof(float) : 0;
+  const size_t g = upsample ? (size_t)batch * h * w * 9 * cout * sizeof(float) : 0;
+  return g + tc_conv_split_bytes(batch, h, w, cin) + 256;
 }
 
 static int check_conv_shapes(const char* who, int batch, int h, int w, int cin, int cout) {
@@ -477,9 +476,7 @@ extern "C" int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const 
                                      const float* d, const float* noise, int64_t noise_batch_stride,
                                      const float* noise_w, const float* act_bias, float* y, int batch,
                                      int h, int w, int cin, int cout, void* scratch,
-                                     size_t scratch_bytes, void* stream) {
-  (void)scratch;
-  (void)scratch_bytes;
+                                     size_t scratch_bytes, uint32_t flags, void* stream) {
   int rc = check_conv_shapes("e3_styled_conv3x3_fwd", batch, h, w, cin, cout);
   if (rc) return rc;
   if (batch == 0) return E3_OK;
@@ -491,6 +488,15 @@ extern "C" int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const 
   a.B = batch, a.H = h, a.W = w, a.Cin = cin, a.N = cout;
   a.mode = act_bias ? 1 : 2, a.d = d, a.noise = noise, a.noise_bstride = noise_batch_stride;
   a.noise_w = noise_w, a.act_bias = act_bias;
+  const bool tcore = use_tensor_cores(flags, batch, h, w, cin, cout);
+  E3_REQUIRE(tcore || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
+             "e3_styled_conv3x3_fwd: E3_CONV_TENSOR_CORES requested for an unsupported shape");
+  if (tcore) {
+    E3_REQUIRE(scratch && scratch_bytes >= e3_styled_conv_scratch_bytes(batch, h, w, cin, cout, 0),
+               E3_ERR_SCRATCH, "e3_styled_conv3x3_fwd: scratch too small");
+    void* split = reinterpret_cast<void*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    return tc_conv_launch(a, 9, packed_bf16_part(wpacked, cout, cin), split, as_stream(stream));
+  }
   const int64_t M = (int64_t)batch * h * w;
   dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (cout + CG_BN - 1) / CG_BN);
   conv_gemm_ffma_kernel<9><<<grid, 256, 0, as_stream(stream)>>>(a);
@@ -503,7 +509,7 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
                                         int64_t noise_batch_stride, const float* noise_w,
                                         const float* act_bias, float* y, int batch, int h, int w,
                                         int cin, int cout, void* scratch, size_t scratch_bytes,
-                                        void* stream) {
+                                        uint32_t flags, void* stream) {
   int rc = check_conv_shapes("e3_styled_conv3x3_up_fwd", batch, h, w, cin, cout);
   if (rc) return rc;
   if (batch == 0) return E3_OK;
@@ -517,10 +523,20 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
   a.x = x, a.s = s, a.wg = static_cast<const float*>(wpacked), a.out = static_cast<float*>(scratch);
   a.B = batch, a.H = h, a.W = w, a.Cin = cin, a.N = 9 * cout;
   a.mode = 0;
-  const int64_t M = (int64_t)batch * h * w;
-  dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (a.N + CG_BN - 1) / CG_BN);
-  conv_gemm_ffma_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a);
-  E3_CUDA(cudaGetLastError());
+  const bool tcore = use_tensor_cores(flags, batch, h, w, cin, a.N);
+  E3_REQUIRE(tcore || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
+             "e3_styled_conv3x3_up_fwd: E3_CONV_TENSOR_CORES requested for an unsupported shape");
+  if (tcore) {
+    char* after_g = static_cast<char*>(scratch) + (size_t)batch * h * w * 9 * cout * sizeof(float);
+    void* split = reinterpret_cast<void*>(((uintptr_t)after_g + 255) & ~(uintptr_t)255);
+    rc = tc_conv_launch(a, 1, packed_bf16_part(wpacked, cout, cin), split, as_stream(stream));
+    if (rc) return rc;
+  } else {
+    const int64_t M = (int64_t)batch * h * w;
+    dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (a.N + CG_BN - 1) / CG_BN);
+    conv_gemm_ffma_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a);
+    E3_CUDA(cudaGetLastError());
+  }
   Col2imArgs c{};
   c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
   c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;

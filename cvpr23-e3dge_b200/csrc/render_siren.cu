@@ -631,10 +631,10 @@ extern "C" int e3_siren_pack(const e3_siren_weights* w, void* packed, void* stre
 
 extern "C" int e3_film_fwd(const void* packed, const float* styles, int batch, int styles_per_image,
                            float* film, void* stream) {
-  E3_REQUIRE(packed && styles && film, E3_ERR_BAD_ARG, "e3_film_fwd: null argument");
   E3_REQUIRE(batch >= 0 && (styles_per_image == 1 || styles_per_image == 9), E3_ERR_BAD_ARG,
              "e3_film_fwd: styles_per_image must be 1 (w) or 9 (w+), got %d", styles_per_image);
-  if (batch == 0) return E3_OK;
+  if (batch == 0) return E3_OK;  // empty batches carry null data pointers
+  E3_REQUIRE(packed && styles && film, E3_ERR_BAD_ARG, "e3_film_fwd: null argument");
   film_kernel<<<batch * 9, 256, 0, as_stream(stream)>>>(static_cast<const float*>(packed), styles,
                                                        styles_per_image, film);
   E3_CUDA(cudaGetLastError());
@@ -646,6 +646,7 @@ extern "C" int e3_render_fwd(const void* packed, const e3_render_params* p, cons
   E3_REQUIRE(packed && p && in && out, E3_ERR_BAD_ARG, "e3_render_fwd: null argument");
   E3_REQUIRE(p->batch >= 0 && p->height > 0 && p->width > 0 && p->res > 0, E3_ERR_BAD_ARG,
              "e3_render_fwd: bad geometry B=%d H=%d W=%d res=%d", p->batch, p->height, p->width, p->res);
+  if (p->batch == 0) return E3_OK;  // empty batches carry null data pointers
   E3_REQUIRE(p->n_samples >= 1 && p->n_samples <= TILE_M, E3_ERR_UNSUPPORTED,
              "e3_render_fwd: n_samples=%d outside [1,%d] (use e3_siren_points_fwd for sdf grids)",
              p->n_samples, TILE_M);
@@ -673,9 +674,9 @@ extern "C" int e3_render_fwd(const void* packed, const e3_render_params* p, cons
 extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
                                    const float* viewdirs, int batch, int n_points, float pts_scale,
                                    float* sdf, float* raw_rgb, float* feat, void* stream) {
-  E3_REQUIRE(packed && film && points && sdf, E3_ERR_BAD_ARG, "e3_siren_points_fwd: null argument");
   E3_REQUIRE(batch >= 0 && n_points >= 0, E3_ERR_BAD_ARG, "e3_siren_points_fwd: negative size");
   if (batch == 0 || n_points == 0) return E3_OK;
+  E3_REQUIRE(packed && film && points && sdf, E3_ERR_BAD_ARG, "e3_siren_points_fwd: null argument");
   RenderArgs a{};
   a.packed = static_cast<const float*>(packed);
   a.p.batch = batch;

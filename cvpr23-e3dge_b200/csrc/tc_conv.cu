@@ -1,0 +1,319 @@
+// Tensor-core (tcgen05) implicit-GEMM for the modulated-conv decoder, sm_100a.
+//
+//   C[pixel, n] = sum_{tap, ci} xs[b, y+dy, x+dx, ci] * Wk[n, tap*Cin + ci]
+//
+// with xs = x * s[b,:] (the per-sample modulation moved onto the activations, see modconv.cu)
+// and both operands split into bf16 hi + lo: three tcgen05.mma passes per k-step
+// (hi*hi, hi*lo, lo*hi) accumulate in fp32 in TMEM, which keeps the decoder within ~1e-5 of
+// the fp32 reference where plain bf16 operands would sit at ~1e-2 (north_star bar: 1e-3).
+//
+// Structure (one CTA per 128-pixel x 128-channel output tile, 6 warps):
+//   warp 0      TMA producer: 4-D tiled tensor maps over the NHWC bf16 activations
+//               (box = 64 ch x bw x bh x bb pixels, 128B swizzle, out-of-bounds = zero fill, which
+//               *is* the conv's zero padding) and 2-D maps over the K-major weights; 3-stage
+//               full/empty mbarrier ring, 64 KB per stage (A_hi, A_lo, B_hi, B_lo);
+//   warp 1      TMEM allocation + single-thread MMA issue (12 UMMAs 128x128x16 per stage),
+//               tcgen05.commit releases the stage / signals the epilogue;
+//   warps 2..5  epilogue: tcgen05.ld (each warp its 32-lane quarter), demodulation + noise +
+//               bias + leaky-ReLU*sqrt(2) (StyledConv, stylesdf_model.py:494-507), fp32 NHWC store.
+#include "tcgen05.cuh"
+#include "modconv.cuh"
+
+namespace e3 {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  E3_REQUIRE(enc != nullptr, E3_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  E3_REQUIRE(r == CUDA_SUCCESS, E3_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return E3_OK;
+}
+
+// xs = x * s[b,:]  ->  bf16 hi / lo, NHWC
+__global__ void __launch_bounds__(256) modulate_split_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ s,
+                                                             __nv_bfloat16* __restrict__ hi,
+                                                             __nv_bfloat16* __restrict__ lo,
+                                                             int64_t n_vec8, int hw, int cin) {
+  const int c8n = cin >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8n) * 8;
+    const int64_t pix = i / c8n;
+    const int b = (int)(pix / hw);
+    const float4 v0 = *reinterpret_cast<const float4*>(x + pix * cin + c);
+    const float4 v1 = *reinterpret_cast<const float4*>(x + pix * cin + c + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(s + (size_t)b * cin + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(s + (size_t)b * cin + c + 4);
+    const float v[8] = {v0.x * s0.x, v0.y * s0.y, v0.z * s0.z, v0.w * s0.w,
+                        v1.x * s1.x, v1.y * s1.y, v1.z * s1.z, v1.w * s1.w};
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tc::split_bf16(v[j], h[j], l[j]);
+    *reinterpret_cast<uint4*>(hi + pix * cin + c) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + pix * cin + c) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// K-major bf16 hi/lo weights:  plain    Wk[o][tap*cin + ci]        = scale * W[o][ci][tap]
+//                              upsample Wk[tap*cout + o][ci]        = scale * W[o][ci][tap]
+__global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int cin, int upsample,
+                                      float scale, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo) {
+  const int64_t total = (int64_t)cout * cin * 9;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int o, ci, tap;
+    if (upsample) {
+      ci = (int)(idx % cin);
+      const int n = (int)(idx / cin);
+      o = n % cout;
+      tap = n / cout;
+    } else {
+      const int k = (int)(idx % ((int64_t)9 * cin));
+      o = (int)(idx / ((int64_t)9 * cin));
+      ci = k % cin;
+      tap = k / cin;
+    }
+    __nv_bfloat16 h, l;
+    tc::split_bf16(scale * w[((size_t)o * cin + ci) * 9 + tap], h, l);
+    hi[idx] = h;
+    lo[idx] = l;
+  }
+}
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = 128 * 128;            // one operand tile: 128 rows x 128 B
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int TC_THREADS = 192;
+
+struct TcTile {
+  int bw, bh, bb, tiles_x, tiles_y, tiles_b;
+};
+
+template <int TAPS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ ConvGemmArgs a, const __grid_constant__ TcTile t) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* accum_bar = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int tx = mt % t.tiles_x, ty = (mt / t.tiles_x) % t.tiles_y, tb = mt / (t.tiles_x * t.tiles_y);
+  const int x0 = tx * t.bw, y0 = ty * t.bh, b0 = tb * t.bb;
+  const int n0 = blockIdx.y * TC_BN;
+  const int kpt = a.Cin / TC_BK, nkb = TAPS * kpt;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&tmA_hi);
+    tc::prefetch_tensormap(&tmA_lo);
+    tc::prefetch_tensormap(&tmB_hi);
+    tc::prefetch_tensormap(&tmB_lo);
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TC_BN);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int tap = kb / kpt, kc = kb - tap * kpt;
+        const int dx = (TAPS == 9) ? tap % 3 - 1 : 0, dy = (TAPS == 9) ? tap / 3 - 1 : 0;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+        uint8_t* st = smem + stage * TC_STAGE_BYTES;
+        tc::tma_load_4d(st, &tmA_hi, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
+        tc::tma_load_4d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
+        tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[stage], tap * a.Cin + kc * TC_BK, n0);
+        tc::tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[stage], tap * a.Cin + kc * TC_BK, n0);
+        if (++stage == TC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, TC_BN);
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc::fence_after_thread_sync();
+        const uint32_t sb = smem_u32(smem + stage * TC_STAGE_BYTES);
+        const uint64_t dA_hi = tc::make_smem_desc_sw128(sb);
+        const uint64_t dA_lo = tc::make_smem_desc_sw128(sb + TC_TILE_BYTES);
+        const uint64_t dB_hi = tc::make_smem_desc_sw128(sb + 2 * TC_TILE_BYTES);
+        const uint64_t dB_lo = tc::make_smem_desc_sw128(sb + 3 * TC_TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 16; ++ks) {
+          const uint64_t ah = tc::advance_desc_k(dA_hi, ks), al = tc::advance_desc_k(dA_lo, ks);
+          const uint64_t bh = tc::advance_desc_k(dB_hi, ks), bl = tc::advance_desc_k(dB_lo, ks);
+          tc::mma_bf16_ss(tmem_base, ah, bh, idesc, (kb | ks) != 0);
+          tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
+          tc::mma_bf16_ss(tmem_base, al, bh, idesc, true);
+        }
+        tc::mma_commit(&empty[stage]);  // the stage is free once these MMAs have read it
+        if (++stage == TC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc::mma_commit(accum_bar);
+    }
+  } else {
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to warp q = warp % 4 =====
+    mbar_wait(accum_bar, 0);
+    tc::fence_after_thread_sync();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ix = m % t.bw, iy = (m / t.bw) % t.bh, ib = m / (t.bw * t.bh);
+    const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
+    const bool valid = b < a.B;
+    const int p = y * a.W + x;
+    const float nw = (a.mode == 1) ? a.noise_w[0] : 0.f;
+    const float nz = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
+    float* orow = a.out + (((size_t)(valid ? b : 0) * a.H + y) * a.W + x) * a.N + n0;
+#pragma unroll 1
+    for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+      float v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + chunk * 32, v);
+      if (!valid) continue;
+      const int nb = n0 + chunk * 32;
+      if (a.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float tt = fmaf(v[j], a.d[(size_t)b * a.N + nb + j], nz) + a.act_bias[nb + j];
+          v[j] = (tt > 0.f ? tt : 0.2f * tt) * 1.41421356237309515f;
+        }
+      } else if (a.mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= a.d[(size_t)b * a.N + nb + j];
+      }
+      float4* dst = reinterpret_cast<float4*>(orow + chunk * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TC_BN);
+}
+
+bool tc_conv_supported(int B, int H, int W, int Cin, int N) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  return B > 0 && pow2(W) && pow2(H) && W >= 8 && H * W >= 64 && Cin % TC_BK == 0 && N % TC_BN == 0;
+}
+
+size_t tc_conv_split_bytes(int B, int H, int W, int Cin) {
+  return (size_t)B * H * W * Cin * 2 * sizeof(__nv_bfloat16);
+}
+
+int tc_conv_pack_weight(const float* weight, int cout, int cin, int upsample, float scale,
+                        void* packed_bf16, cudaStream_t stream) {
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(packed_bf16);
+  __nv_bfloat16* lo = hi + (size_t)cout * cin * 9;
+  const int64_t total = (int64_t)cout * cin * 9;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > sm_count() * 32) blocks = sm_count() * 32;
+  conv_pack_bf16_kernel<<<blocks, 256, 0, stream>>>(weight, cout, cin, upsample, scale, hi, lo);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+// a: x, s, out, B, H, W, Cin, N, epilogue fields filled by the caller; a.wg is unused here.
+int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, void* split_scratch,
+                   cudaStream_t stream) {
+  E3_REQUIRE(tc_conv_supported(a.B, a.H, a.W, a.Cin, a.N), E3_ERR_UNSUPPORTED,
+             "tensor-core conv: unsupported shape B=%d H=%d W=%d Cin=%d N=%d (needs power-of-two "
+             "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0)", a.B, a.H, a.W, a.Cin, a.N);
+  const size_t n_act = (size_t)a.B * a.H * a.W * a.Cin;
+  __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
+  __nv_bfloat16* xs_lo = xs_hi + n_act;
+  {
+    const int64_t nv = (int64_t)(n_act / 8);
+    int blocks = (int)((nv + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    modulate_split_kernel<<<blocks, 256, 0, stream>>>(a.x, a.s, xs_hi, xs_lo, nv, a.H * a.W, a.Cin);
+    E3_CUDA(cudaGetLastError());
+  }
+  TcTile t;
+  t.bw = a.W < 128 ? a.W : 128;
+  t.bh = (128 / t.bw) < a.H ? (128 / t.bw) : a.H;
+  t.bb = 128 / (t.bw * t.bh);
+  t.tiles_x = a.W / t.bw;
+  t.tiles_y = a.H / t.bh;
+  t.tiles_b = (a.B + t.bb - 1) / t.bb;
+
+  const int K = taps * a.Cin;
+  const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(packed_bf16);
+  const __nv_bfloat16* w_lo = w_hi + (size_t)a.N * K;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  const uint64_t adims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t astr[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+  const uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)t.bw, (uint32_t)t.bh, (uint32_t)t.bb};
+  const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)a.N};
+  const uint64_t bstr[1] = {(uint64_t)K * 2};
+  const uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)TC_BN};
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA_hi, xs_hi, 4, adims, astr, abox))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmA_lo, xs_lo, 4, adims, astr, abox))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox))) return rc;
+
+  static thread_local bool attr_set[2] = {false, false};
+  const int which = taps == 9 ? 1 : 0;
+  if (!attr_set[which]) {
+    const void* fn = which ? (const void*)tc_conv_kernel<9> : (const void*)tc_conv_kernel<1>;
+    E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set[which] = true;
+  }
+  dim3 grid(t.tiles_x * t.tiles_y * t.tiles_b, a.N / TC_BN);
+  if (taps == 9)
+    tc_conv_kernel<9><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a, t);
+  else
+    tc_conv_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a, t);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+}  // namespace e3

@@ -1,0 +1,145 @@
+// tcgen05 / TMEM / TMA-tensor building blocks for sm_100a (inline PTX; no CUTLASS dependency).
+//
+// Conventions used by every tensor-core kernel in this library:
+//   * operands are bf16, K-major, in shared memory in the canonical SWIZZLE_128B layout:
+//     rows of 64 elements (128 B), 8-row atoms of 1024 B, 16-byte chunk index XOR (row % 8).
+//     This is exactly what a TMA tiled load with CU_TENSOR_MAP_SWIZZLE_128B writes.
+//   * accumulators are fp32 in TMEM: lane = tile row (M = 128), column = tile column;
+//   * "split-bf16" (fp32-faithful) products: x = hi + lo with hi = bf16(x), lo = bf16(x - hi);
+//     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, all three accumulated in fp32 in TMEM
+//     (relative error per product ~2^-16, vs 2^-8 for plain bf16 and 2^-11 for tf32).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace e3 {
+namespace tc {
+
+// ---- TMEM management (one warp allocates, the same warp frees) ----------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void fence_before_thread_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_thread_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---- descriptors -----------------------------------------------------------------------------
+// Instruction descriptor, kind::f16, A/B = bf16 (K-major), D = fp32, M x N tile.
+//   bits [4,6) c_format = 1 (F32); [7,10) a_format = 1 (BF16); [10,13) b_format = 1 (BF16);
+//   bit 15 a_major = 0 (K); bit 16 b_major = 0 (K); [17,23) N >> 3; [24,29) M >> 4.
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor for a K-major SWIZZLE_128B operand tile whose rows are
+// 128 B apart and whose 8-row atoms are 1024 B apart:
+//   [0,14) start address >> 4; [16,30) leading byte offset >> 4 (= 1, unused with swizzle);
+//   [32,46) stride byte offset >> 4 (= 1024 >> 4); [46,48) version = 1 (sm_100);
+//   [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// advance along K inside the 128-byte swizzle row: +32 B per UMMA_K = 16 bf16
+__device__ __forceinline__ uint64_t advance_desc_k(uint64_t desc, int k16_steps) {
+  return desc + (uint64_t)(k16_steps * 2);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Arrive on an mbarrier when all previously issued MMAs of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMEM -> registers: 32 lanes (this warp's quarter) x 32 consecutive fp32 columns -----------
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- TMA tiled tensor loads (SASS: UTMALDG) -------------------------------------------------------
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// split fp32 -> (hi, lo) bf16
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+}  // namespace tc
+
+// ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) -------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+// bf16 tensor, innermost dim first; strides in bytes for dims 1..rank-1; 128B swizzle, zero OOB fill.
+int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);
+
+}  // namespace e3

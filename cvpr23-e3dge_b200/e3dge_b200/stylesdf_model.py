@@ -147,6 +147,10 @@ class _PackedConv:
         return wp, wsq
 
 
+CONV_BACKENDS = {"auto": _lib.CONV_AUTO, "fp32": _lib.CONV_FP32_CUDA_CORES,
+                 "tensor_cores": _lib.CONV_TENSOR_CORES}
+
+
 def _to_nhwc(x):
     lib = _lib.load()
     x = _lib.as_f32c(x)
@@ -212,6 +216,9 @@ class ModulatedConv2d(nn.Module):
         self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
         self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
         self.demodulate = demodulate
+        # "auto": tcgen05 split-bf16 when the shape allows, else exact-fp32 CUDA cores;
+        # "fp32" / "tensor_cores" force one of them (include/e3dge_b200.h E3_CONV_*)
+        self.backend = "auto"
         self._packed = _PackedConv()
 
     def styles(self, latent):
@@ -275,7 +282,7 @@ def _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias):
     fn = lib.e3_styled_conv3x3_up_fwd if up else lib.e3_styled_conv3x3_fwd
     args = (_lib.ptr(x), _lib.ptr(wp), _lib.ptr(s), _lib.ptr(d), _lib.ptr(noise), nstride,
             _lib.ptr(noise_w), _lib.ptr(act_bias), _lib.ptr(y), b, h, w, cin, cout,
-            _lib.ptr(scratch), nbytes, _lib.cur_stream())
+            _lib.ptr(scratch), nbytes, CONV_BACKENDS[conv.backend], _lib.cur_stream())
     _lib.check(fn(*args), "e3_styled_conv3x3_up_fwd" if up else "e3_styled_conv3x3_fwd")
     return y
 

@@ -188,10 +188,19 @@ int e3_nhwc_to_nchw(const float* x, float* y, int batch, int ch, int h, int w, v
 /* Library-private packed image of one 3x3 conv weight [cout,cin,3,3] (reference layout,
  * `decoder.*.conv.weight` without its leading 1): the equalised-lr scale 1/sqrt(cin*9)
  * (stylesdf_model.py:301-302) is folded in and the taps are laid out GEMM-major
- * (plain: [tap][cin][cout]; upsample: [cin][tap*cout]).  Pack once per weight update. */
+ * (plain: [tap][cin][cout]; upsample: [cin][tap*cout]), followed by the K-major bf16 hi/lo
+ * split the tensor-core path reads through TMA.  Pack once per weight update. */
 size_t e3_conv_packed_bytes(int cout, int cin);
 int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample, void* packed,
                         void* stream);
+
+/* arithmetic selection for the 3x3 modulated convs (flags argument) */
+#define E3_CONV_AUTO 0u            /* tensor cores when the shape allows, else CUDA cores */
+#define E3_CONV_FP32_CUDA_CORES 1u /* exact-fp32 FFMA implicit GEMM */
+#define E3_CONV_TENSOR_CORES 2u    /* tcgen05 split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate in
+                                      TMEM); E3_ERR_UNSUPPORTED unless H, W are powers of two >= 8,
+                                      cin % 64 == 0 and the GEMM N (cout, or 9*cout when upsampling)
+                                      % 128 == 0 */
 
 /* StyledConv forward, plain 3x3 (stylesdf_model.py:356-360, 494-507):
  *   y = lrelu_0.2( d[b,o] * conv3x3(x * s[b,:], W/sqrt(cin*9)) + noise_w*noise[y,x]
@@ -205,7 +214,7 @@ int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const float* s, c
                           const float* noise, int64_t noise_batch_stride,
                           const float* noise_w, const float* act_bias, float* y, int batch,
                           int h, int w, int cin, int cout, void* scratch,
-                          size_t scratch_bytes, void* stream);
+                          size_t scratch_bytes, uint32_t flags, void* stream);
 
 /* StyledConv forward, upsampling (stylesdf_model.py:331-346, 283-291): conv_transpose2d
  * stride 2 followed by the 4x4 [1,3,3,1] blur (gain 4, pad (1,1)), then noise + bias +
@@ -216,7 +225,7 @@ int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, const float* s
                              int64_t noise_batch_stride, const float* noise_w,
                              const float* act_bias, float* y, int batch, int h, int w,
                              int cin, int cout, void* scratch, size_t scratch_bytes,
-                             void* stream);
+                             uint32_t flags, void* stream);
 size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout, int upsample);
 
 /* ToRGB forward (stylesdf_model.py:531-541, Upsample :96-119): 1x1 modulated conv without

@@ -253,3 +253,66 @@ def test_full_size_properties():
     assert torch.isfinite(out["gen_imgs"]).all() and out["gen_imgs"].shape == (B, 3, size, size)
     # depth is a convex combination of the sample depths
     assert out["depth"].min().item() >= 0.88 - 1e-5 and out["depth"].max().item() <= 1.12 + 1e-5
+
+
+def _set_backend(module, backend):
+    from e3dge_b200.stylesdf_model import ModulatedConv2d
+    for m in module.modules():
+        if isinstance(m, ModulatedConv2d):
+            m.backend = backend
+
+
+@pytest.mark.parametrize("cin,cout,hw,batch,up", [
+    (64, 128, 16, 2, False), (64, 128, 16, 2, True),      # 16x8-pixel tiles
+    (128, 128, 8, 3, False), (128, 128, 8, 3, True),      # 8x8 maps: two images per tile, odd batch
+    (256, 512, 64, 1, False), (512, 256, 64, 1, True),    # conv1 / first up-conv of the 256^2 decoder
+    (128, 128, 256, 1, False),                            # last conv: 128-wide row tiles
+])
+def test_tensor_core_conv_vs_fp32_path_and_oracle(cin, cout, hw, batch, up):
+    from e3dge_b200.stylesdf_model import StyledConv
+    g = np.random.Generator(np.random.PCG64(cin * 7 + cout + hw + batch))
+    f32 = lambda *s: torch.from_numpy(g.standard_normal(s).astype(np.float32))
+    m = StyledConv(cin, cout, 3, 512, upsample=up)
+    sd = {"conv.weight": f32(1, cout, cin, 3, 3), "conv.modulation.weight": f32(cin, 512),
+          "conv.modulation.bias": 1 + 0.1 * f32(cin), "noise.weight": 0.1 * f32(1),
+          "activate.bias": 0.1 * f32(cout), "bias": torch.zeros(1, cout, 1, 1)}
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda()
+    x, lat = f32(batch, cin, hw, hw), f32(batch, 512)
+    oh = hw * 2 if up else hw
+    noise = f32(1, 1, oh, oh)
+    with torch.no_grad():
+        _set_backend(m, "tensor_cores")
+        y_tc = m(x.cuda(), lat.cuda(), noise=noise.cuda())
+        _set_backend(m, "fp32")
+        y_fp = m(x.cuda(), lat.cuda(), noise=noise.cuda())
+        osd = {"decoder.x." + k: v for k, v in sd.items()}
+        y_ref = None
+        if hw <= 64:  # the CPU oracle finishes in seconds at these sizes
+            y_ref = O.styled_conv(x, lat, noise, osd, "decoder.x.", upsample=up)
+    assert y_tc.shape == y_fp.shape == (batch, cout, oh, oh)
+    assert rel_linf(y_tc.cpu(), y_fp.cpu()) < 1e-4, "tensor-core vs exact-fp32 CUDA-core path"
+    if y_ref is not None:
+        assert rel_linf(y_fp.cpu(), y_ref) < 1e-4
+        assert rel_linf(y_tc.cpu(), y_ref) < 1e-4
+
+
+def test_tensor_core_request_on_unsupported_shape_fails_loudly():
+    from e3dge_b200.stylesdf_model import StyledConv
+    m = StyledConv(16, 24, 3, 512).cuda()
+    _set_backend(m, "tensor_cores")
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        m(torch.randn(1, 16, 10, 10, device="cuda"), torch.randn(1, 512, device="cuda"))
+
+
+def test_decoder_backends_agree_at_full_size():
+    size, res, seed = 256, 64, 321
+    G, sd = _build(size, res, seed, "default")
+    inp = _cuda(P.make_inputs(seed, 2, decoder_layout(size, res), res))
+    feats = torch.randn(2, 256, res, res, device="cuda") * 0.3
+    with torch.no_grad():
+        _set_backend(G, "tensor_cores")
+        a, _ = G.decoder(feats, [inp["w_dec"]], input_is_latent=True, randomize_noise=False)
+        _set_backend(G, "fp32")
+        b, _ = G.decoder(feats, [inp["w_dec"]], input_is_latent=True, randomize_noise=False)
+    assert rel_linf(a.cpu(), b.cpu()) < 1e-4
