@@ -20,44 +20,11 @@
 //     cp.async.bulk (TMA, SASS UBLKCP) through a 4-stage full/empty mbarrier ring;
 //   * sdf / rgb heads use warp-shuffle reductions; the S-step transmittance scan and the
 //     weighted sums run out of shared memory; outputs are written once.
-#include "common.cuh"
+#include <cuda_bf16.h>
+
+#include "render_siren.cuh"
 
 namespace e3 {
-
-constexpr int SW = 256;                        // SIREN width
-constexpr int TILE_M = 96;                     // sample rows per tile
-constexpr int ACT_LD = 100;                    // padded row stride of h[n][m] (bank-conflict free)
-constexpr int KCHUNK = 16;                     // k rows per TMA slab
-constexpr int STAGES = 4;
-constexpr int CHUNK_FLOATS = KCHUNK * SW;      // 4096 floats = 16 KB
-constexpr int CHUNKS_PER_LAYER = SW / KCHUNK;  // 16
-constexpr int N_CONSUMER_WARPS = 8;
-constexpr int N_CONSUMERS = N_CONSUMER_WARPS * 32;
-constexpr int N_THREADS = N_CONSUMERS + 32;
-
-// ---- packed weight image (floats) -----------------------------------------------------
-// "p-order": column p of a packed slab holds output channel n(p) so that one lane's 8
-// accumulator columns are two LDS.128 and the epilogue stores are conflict free.
-constexpr int OFF_W0P = 0;                      // [3][256]   layer 0, p-order
-constexpr int OFF_WVD = OFF_W0P + 3 * SW;       // [3][256]   view layer, view-dir inputs, p-order
-constexpr int OFF_BIAS = OFF_WVD + 3 * SW;      // [9][256]   natural order (8 trunk + view)
-constexpr int OFF_WSIG = OFF_BIAS + 9 * SW;     // [256]
-constexpr int OFF_WRGB = OFF_WSIG + SW;         // [3][256]
-constexpr int OFF_HEADB = OFF_WRGB + 3 * SW;    // bsig, brgb[3], pad -> 32
-constexpr int SMALL_FLOATS = OFF_HEADB + 32;    // 4896
-constexpr int OFF_STREAM = SMALL_FLOATS;        // [8][256][256] layers 1..7 + view, p-order
-constexpr int OFF_GAMMA_W = OFF_STREAM + 8 * SW * SW;  // [9][256][256] natural (out,in)
-constexpr int OFF_GAMMA_B = OFF_GAMMA_W + 9 * SW * SW;
-constexpr int OFF_BETA_W = OFF_GAMMA_B + 9 * SW;
-constexpr int OFF_BETA_B = OFF_BETA_W + 9 * SW * SW;
-constexpr int PACKED_FLOATS = OFF_BETA_B + 9 * SW;
-static_assert((OFF_STREAM * 4) % 128 == 0, "weight stream must be 128B aligned");
-
-__host__ __device__ __forceinline__ int chan_of_packed_col(int p) {
-  // p = 128*q + 4*lane + jj  ->  n = lane + 32*(jj + 4*q)
-  const int q = p >> 7, lane = (p & 127) >> 2, jj = p & 3;
-  return lane + 32 * (jj + 4 * q);
-}
 
 __global__ void siren_pack_kernel(e3_siren_weights w, float* __restrict__ packed) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,9 +59,39 @@ __global__ void siren_pack_kernel(e3_siren_weights w, float* __restrict__ packed
   } else if (idx < OFF_BETA_B) {
     const int r = idx - OFF_BETA_W;
     v = w.beta_w[r / (SW * SW)][r % (SW * SW)];
-  } else {
+  } else if (idx < OFF_W0N) {
     const int r = idx - OFF_BETA_B;
     v = w.beta_b[r / SW][r % SW];
+  } else if (idx < OFF_WVDN) {
+    const int r = idx - OFF_W0N;
+    v = w.pts_w[0][(r % SW) * 3 + r / SW];
+  } else if (idx < OFF_WVDN + 3 * SW) {
+    const int r = idx - OFF_WVDN;
+    v = w.views_w[(r % SW) * 259 + 256 + r / SW];
+  } else if (idx < OFF_TC_STREAM) {
+    v = 0.f;  // alignment padding
+  } else {
+    // two bf16 per float slot of the tensor-core stream
+    const int e0 = (idx - OFF_TC_STREAM) * 2;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = e0 + h;                       // bf16 element index in the stream
+      const int tile = e / (128 * 64), in_tile = e % (128 * 64);
+      const int nh = tile & 1, is_lo = (tile >> 1) & 1, kb = (tile >> 2) & 3, l = tile >> 4;
+      // invert the swizzled placement: byte offset -> (row r, k within block)
+      const int byte = in_tile * 2;
+      const int r = (byte >> 10) * 8 + ((byte >> 7) & 7);
+      const int chunk = ((byte >> 4) & 7) ^ (r & 7);
+      const int kk = chunk * 8 + ((byte >> 1) & 7);
+      const int n = nh * 128 + r, k = kb * 64 + kk;
+      const float wv = (l < 7) ? w.pts_w[l + 1][n * SW + k] : w.views_w[n * 259 + k];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+      const uint16_t u = is_lo ? __bfloat16_as_ushort(lo) : __bfloat16_as_ushort(hi);
+      bits |= (uint32_t)u << (16 * h);
+    }
+    v = __uint_as_float(bits);
   }
   packed[idx] = v;
 }
@@ -113,7 +110,7 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ pac
   for (int i = 0; i < 8; ++i) s[i] = st[lane + 32 * i];
   const float* gw = packed + OFF_GAMMA_W + (size_t)l * SW * SW;
   const float* bw = packed + OFF_BETA_W + (size_t)l * SW * SW;
-  float* out = film + ((size_t)b * 9 + l) * 2 * SW;
+  float* out = film + ((size_t)b * 9 + l) * FILM_ROWS * SW;
   for (int n = warp; n < SW; n += 8) {
     float g = 0.f, be = 0.f;
 #pragma unroll
@@ -125,28 +122,14 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ pac
     be = warp_sum(be);
     if (lane == 0) {
       // LinearLayer: std_init*(Wx+b)+bias_init  (volume_renderer.py:76-80,107-114)
-      out[n] = 15.f * (g + packed[OFF_GAMMA_B + l * SW + n]) + 30.f;
-      out[SW + n] = 0.25f * (be + packed[OFF_BETA_B + l * SW + n]);
+      const float gam = 15.f * (g + packed[OFF_GAMMA_B + l * SW + n]) + 30.f;
+      const float bet = 0.25f * (be + packed[OFF_BETA_B + l * SW + n]);
+      out[n] = gam;
+      out[SW + n] = bet;
+      out[2 * SW + n] = fmaf(gam, packed[OFF_BIAS + l * SW + n], bet);  // layer bias folded
     }
   }
 }
-
-// ---- kernel arguments -------------------------------------------------------------------
-struct RenderArgs {
-  const float* packed;
-  e3_render_params p;
-  e3_render_inputs in;
-  e3_render_outputs out;
-  int rays_per_tile, tiles_per_image, n_tiles;
-  // explicit-points mode
-  const float* points;
-  const float* pviewdirs;
-  int n_points;
-  float* p_sdf;
-  float* p_rgb;
-  float* p_feat;
-  int with_view;  // 0: stop after the sdf head (sdf-only query)
-};
 
 struct Smem {
   float act[SW * ACT_LD];             // h[n][m]
@@ -320,8 +303,9 @@ siren_render_kernel(const __grid_constant__ RenderArgs a) {
     const size_t samp0 = ((size_t)b * HW + unit0) * S;  // first sample row in [B,HW,S]
 
     if (b != cur_b) {
-      const float* f = a.in.film + (size_t)b * 9 * 2 * SW;
-      for (int i = tid; i < 9 * 2 * SW; i += N_CONSUMERS) sm.film[i] = f[i];
+      const float* f = a.in.film + (size_t)b * 9 * FILM_ROWS * SW;
+      for (int i = tid; i < 9 * 2 * SW; i += N_CONSUMERS)
+        sm.film[i] = f[(i / (2 * SW)) * FILM_ROWS * SW + (i % (2 * SW))];
       cur_b = b;
     }
 
@@ -647,9 +631,11 @@ extern "C" int e3_render_fwd(const void* packed, const e3_render_params* p, cons
   E3_REQUIRE(p->batch >= 0 && p->height > 0 && p->width > 0 && p->res > 0, E3_ERR_BAD_ARG,
              "e3_render_fwd: bad geometry B=%d H=%d W=%d res=%d", p->batch, p->height, p->width, p->res);
   if (p->batch == 0) return E3_OK;  // empty batches carry null data pointers
-  E3_REQUIRE(p->n_samples >= 1 && p->n_samples <= TILE_M, E3_ERR_UNSUPPORTED,
+  const bool ffma = (p->flags & E3_RENDER_FP32_CUDA_CORES) != 0;
+  const int tile_m = ffma ? TILE_M : 128;
+  E3_REQUIRE(p->n_samples >= 1 && p->n_samples <= tile_m, E3_ERR_UNSUPPORTED,
              "e3_render_fwd: n_samples=%d outside [1,%d] (use e3_siren_points_fwd for sdf grids)",
-             p->n_samples, TILE_M);
+             p->n_samples, tile_m);
   E3_REQUIRE(in->cam_poses && in->focal && in->near && in->far && in->pix_x && in->pix_y && in->film,
              E3_ERR_BAD_ARG, "e3_render_fwd: missing camera / film input");
   E3_REQUIRE(in->t_vals || in->z_jitter, E3_ERR_BAD_ARG, "e3_render_fwd: need t_vals or z_jitter");
@@ -663,17 +649,18 @@ extern "C" int e3_render_fwd(const void* packed, const e3_render_params* p, cons
   a.p = *p;
   a.in = *in;
   a.out = *out;
-  a.rays_per_tile = TILE_M / p->n_samples;
+  a.rays_per_tile = tile_m / p->n_samples;
   const int hw = p->height * p->width;
   a.tiles_per_image = (hw + a.rays_per_tile - 1) / a.rays_per_tile;
   a.n_tiles = a.tiles_per_image * p->batch;
   a.with_view = 1;
-  return launch_render(a, 0, as_stream(stream));
+  return ffma ? launch_render(a, 0, as_stream(stream)) : launch_render_tc(a, 0, as_stream(stream));
 }
 
 extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
                                    const float* viewdirs, int batch, int n_points, float pts_scale,
-                                   float* sdf, float* raw_rgb, float* feat, void* stream) {
+                                   float* sdf, float* raw_rgb, float* feat, uint32_t flags,
+                                   void* stream) {
   E3_REQUIRE(batch >= 0 && n_points >= 0, E3_ERR_BAD_ARG, "e3_siren_points_fwd: negative size");
   if (batch == 0 || n_points == 0) return E3_OK;
   E3_REQUIRE(packed && film && points && sdf, E3_ERR_BAD_ARG, "e3_siren_points_fwd: null argument");
@@ -689,9 +676,11 @@ extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const 
   a.p_sdf = sdf;
   a.p_rgb = raw_rgb;
   a.p_feat = feat;
-  a.rays_per_tile = TILE_M;
-  a.tiles_per_image = (n_points + TILE_M - 1) / TILE_M;
+  const bool ffma = (flags & E3_RENDER_FP32_CUDA_CORES) != 0;
+  const int tile_m = ffma ? TILE_M : 128;
+  a.rays_per_tile = tile_m;
+  a.tiles_per_image = (n_points + tile_m - 1) / tile_m;
   a.n_tiles = a.tiles_per_image * batch;
   a.with_view = (raw_rgb || feat) ? 1 : 0;
-  return launch_render(a, 1, as_stream(stream));
+  return ffma ? launch_render(a, 1, as_stream(stream)) : launch_render_tc(a, 1, as_stream(stream));
 }

@@ -1,0 +1,73 @@
+// Shared by the CUDA-core (render_siren.cu) and tensor-core (render_siren_tc.cu) renderers:
+// packed weight image layout and kernel argument block.
+#pragma once
+#include "common.cuh"
+
+namespace e3 {
+
+constexpr int SW = 256;                        // SIREN width
+constexpr int TILE_M = 96;                     // sample rows per tile
+constexpr int ACT_LD = 100;                    // padded row stride of h[n][m] (bank-conflict free)
+constexpr int KCHUNK = 16;                     // k rows per TMA slab
+constexpr int STAGES = 4;
+constexpr int CHUNK_FLOATS = KCHUNK * SW;      // 4096 floats = 16 KB
+constexpr int CHUNKS_PER_LAYER = SW / KCHUNK;  // 16
+constexpr int N_CONSUMER_WARPS = 8;
+constexpr int N_CONSUMERS = N_CONSUMER_WARPS * 32;
+constexpr int N_THREADS = N_CONSUMERS + 32;
+
+// ---- packed weight image (floats) -----------------------------------------------------
+// "p-order": column p of a packed slab holds output channel n(p) so that one lane's 8
+// accumulator columns are two LDS.128 and the epilogue stores are conflict free.
+constexpr int OFF_W0P = 0;                      // [3][256]   layer 0, p-order
+constexpr int OFF_WVD = OFF_W0P + 3 * SW;       // [3][256]   view layer, view-dir inputs, p-order
+constexpr int OFF_BIAS = OFF_WVD + 3 * SW;      // [9][256]   natural order (8 trunk + view)
+constexpr int OFF_WSIG = OFF_BIAS + 9 * SW;     // [256]
+constexpr int OFF_WRGB = OFF_WSIG + SW;         // [3][256]
+constexpr int OFF_HEADB = OFF_WRGB + 3 * SW;    // bsig, brgb[3], pad -> 32
+constexpr int SMALL_FLOATS = OFF_HEADB + 32;    // 4896
+constexpr int OFF_STREAM = SMALL_FLOATS;        // [8][256][256] layers 1..7 + view, p-order
+constexpr int OFF_GAMMA_W = OFF_STREAM + 8 * SW * SW;  // [9][256][256] natural (out,in)
+constexpr int OFF_GAMMA_B = OFF_GAMMA_W + 9 * SW * SW;
+constexpr int OFF_BETA_W = OFF_GAMMA_B + 9 * SW;
+constexpr int OFF_BETA_B = OFF_BETA_W + 9 * SW * SW;
+constexpr int OFF_W0N = OFF_BETA_B + 9 * SW;    // [3][256]  layer 0, natural channel order
+constexpr int OFF_WVDN = OFF_W0N + 3 * SW;      // [3][256]  view-dir inputs, natural order
+// tensor-core weight stream: bf16, pre-swizzled SWIZZLE_128B K-major tiles of 128 (n) x 64 (k),
+// in consumption order [layer 0..7][k-block 0..3][hi, lo][n-half 0..1]; 16 KB per tile.
+constexpr int TC_TILE_BYTES = 128 * 64 * 2;
+constexpr int TC_TILES_PER_LAYER = 16;
+constexpr int OFF_TC_STREAM = ((OFF_WVDN + 3 * SW + 31) / 32) * 32;  // floats; 8*16*16 KB = 2 MB follow
+constexpr int TC_STREAM_FLOATS = 8 * TC_TILES_PER_LAYER * TC_TILE_BYTES / 4;
+constexpr int PACKED_FLOATS = OFF_TC_STREAM + TC_STREAM_FLOATS;
+static_assert((OFF_STREAM * 4) % 128 == 0, "weight stream must be 128B aligned");
+static_assert((OFF_TC_STREAM * 4) % 128 == 0, "tensor-core weight stream must be 128B aligned");
+constexpr int FILM_ROWS = 3;  // per layer: gamma, beta, beta' = gamma*bias + beta (bias folded)
+
+__host__ __device__ __forceinline__ int chan_of_packed_col(int p) {
+  // p = 128*q + 4*lane + jj  ->  n = lane + 32*(jj + 4*q)
+  const int q = p >> 7, lane = (p & 127) >> 2, jj = p & 3;
+  return lane + 32 * (jj + 4 * q);
+}
+
+// ---- kernel arguments -------------------------------------------------------------------
+struct RenderArgs {
+  const float* packed;
+  e3_render_params p;
+  e3_render_inputs in;
+  e3_render_outputs out;
+  int rays_per_tile, tiles_per_image, n_tiles;
+  // explicit-points mode
+  const float* points;
+  const float* pviewdirs;
+  int n_points;
+  float* p_sdf;
+  float* p_rgb;
+  float* p_feat;
+  int with_view;  // 0: stop after the sdf head (sdf-only query)
+};
+
+
+int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream);
+
+}  // namespace e3

@@ -1,0 +1,541 @@
+// Tensor-core (tcgen05) variant of the fused StyleSDF volume renderer, sm_100a.
+//
+// Same contract, inputs and outputs as render_siren.cu (rays -> samples -> 8 x FiLM-SIREN ->
+// sdf head -> view layer -> rgb head -> SDF->sigma -> alpha composite, ONE persistent kernel);
+// the eight 256x256 hidden-layer contractions run on the 5th-gen tensor cores instead of the
+// FFMA pipe:
+//
+//   * a tile = 128 sample rows (UMMA M = 128) = floor(128/S) whole rays;
+//   * the hidden state lives in shared memory as the UMMA A operand: bf16 hi + bf16 lo
+//     (h = hi + lo to 2^-17), K-major SWIZZLE_128B, 4 k-blocks x 16 KB each — written in place
+//     by the epilogue of the previous layer;
+//   * per layer D[128x256] (fp32, 256 TMEM columns) = h_hi*W_hi^T + h_lo*W_hi^T + h_hi*W_lo^T:
+//     96 tcgen05.mma 128x128x16 issued by one thread; the three-product split keeps the result
+//     fp32-faithful (measured 5e-5..1.5e-4 end to end vs 2..5e-2 for plain bf16 operands; the
+//     parity bar is 1e-3);
+//   * weights: 2 MB of pre-split, pre-swizzled bf16 tiles streamed from L2 by cp.async.bulk
+//     (TMA) through a 4 x 16 KB full/empty mbarrier ring, one 128(n) x 64(k) tile per stage;
+//   * 8 epilogue warps (each TMEM lane quarter twice, half the columns each): tcgen05.ld ->
+//     FiLM (bias folded into beta') -> accurate sin -> hi/lo split -> swizzled st.shared of the
+//     next layer's A operand; layer 0 (K = 3), the sdf / rgb heads, the view-direction rank-3
+//     update, the transmittance scan and the weighted feature sum stay on the CUDA cores.
+//
+// Warp roles: warp 0 = TMA weight producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 =
+// compute.  MMA and epilogue of one tile are serialised by the layer-to-layer data dependence
+// (layer l+1 contracts over ALL outputs of layer l); the sdf->alpha->scan work of a tile
+// overlaps with the view-layer MMAs.
+#include <cuda_bf16.h>
+
+#include "render_siren.cuh"
+#include "tcgen05.cuh"
+
+namespace e3 {
+
+constexpr int TCM = 128;                 // rows per tile
+constexpr int TC_RING = 4;               // weight stages
+constexpr int TC_COMPUTE_WARPS = 8;
+constexpr int TC_COMPUTE = TC_COMPUTE_WARPS * 32;
+constexpr int TC_NTHREADS = 64 + TC_COMPUTE;  // producer warp + MMA warp + compute warps
+constexpr int A_KBLOCK_BYTES = TCM * 128;      // 128 rows x 64 bf16
+constexpr int A_BYTES = 4 * A_KBLOCK_BYTES;    // one of hi / lo: 64 KB
+
+struct SmemTC {
+  uint8_t a_hi[A_BYTES];  // also the fp32 [256][128] composite buffer together with a_lo
+  uint8_t a_lo[A_BYTES];
+  uint8_t ring[TC_RING * TC_TILE_BYTES];
+  float z[TCM], dist[TCM], alpha[TCM], wgt[TCM], vis[TCM];
+  float sdf_part[2][TCM];
+  float rgb_part[2][3][TCM];
+  float ray_o[3][TCM], ray_d[3][TCM];
+  uint64_t full[TC_RING], empty[TC_RING];
+  uint64_t a_ready, d_ready;
+  uint32_t tmem_slot;
+};
+static_assert(sizeof(SmemTC) + 1024 <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void compute_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// byte offset of 16-byte chunk `c16` (8 consecutive k) of row m inside one swizzled k-block
+__device__ __forceinline__ uint32_t a_chunk_off(int m, int c16) {
+  return (uint32_t)((m >> 3) * 1024 + (m & 7) * 128 + ((c16 ^ (m & 7)) << 4));
+}
+
+// 8 consecutive outputs v[0..7] (channels n0..n0+7 of row m) -> next layer's A operand
+__device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  const uint32_t off = (uint32_t)(n0 >> 6) * A_KBLOCK_BYTES + a_chunk_off(m, (n0 & 63) >> 3);
+  *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_NTHREADS, 1)
+siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemTC& sm = *reinterpret_cast<SmemTC*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TC_RING; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(&sm.a_ready, TC_COMPUTE_WARPS);
+    mbar_init(&sm.d_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 256);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = sm.tmem_slot;
+
+  const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int gemm_layers = a.with_view ? 8 : 7;
+
+  if (warp == 0) {
+    // ===== TMA producer: 16 weight tiles per layer, in consumption order =====
+    if (lane == 0) {
+      const uint8_t* stream = reinterpret_cast<const uint8_t*>(a.packed + OFF_TC_STREAM);
+      const int per_tile = gemm_layers * TC_TILES_PER_LAYER;
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        for (int c = 0; c < per_tile; ++c) {
+          mbar_wait(&sm.empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&sm.full[stage], TC_TILE_BYTES);
+          tma_bulk_g2s(sm.ring + stage * TC_TILE_BYTES, stream + (size_t)c * TC_TILE_BYTES,
+                       TC_TILE_BYTES, &sm.full[stage]);
+          if (++stage == TC_RING) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16_f32(128, 128);
+      const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
+      uint32_t stage = 0, phase = 0, pa = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        for (int l = 0; l < gemm_layers; ++l) {
+          mbar_wait(&sm.a_ready, pa);  // this layer's A operand is in shared memory
+          pa ^= 1;
+          tc::fence_after_thread_sync();
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
+            const uint64_t dAl = tc::make_smem_desc_sw128(a_lo0 + kb * A_KBLOCK_BYTES);
+#pragma unroll
+            for (int tl = 0; tl < 4; ++tl) {  // (hi,n0) (hi,n1) (lo,n0) (lo,n1)
+              const int is_lo = tl >> 1, nh = tl & 1;
+              mbar_wait(&sm.full[stage], phase);
+              tc::fence_after_thread_sync();
+              const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
+              const uint32_t d = tmem_base + nh * 128;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bk = tc::advance_desc_k(dB, ks);
+                if (!is_lo) {
+                  tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
+                  tc::mma_bf16_ss(d, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+                } else {
+                  tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, true);
+                }
+              }
+              tc::mma_commit(&sm.empty[stage]);
+              if (++stage == TC_RING) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          tc::mma_commit(&sm.d_ready);
+        }
+      }
+    }
+  } else {
+    // ===== compute warps =====
+    const e3_render_params& P = a.p;
+    const int ct = tid - 64;              // 0..255
+    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    const int ch = (warp - 2) >> 2;       // column half: 0 -> channels [0,128), 1 -> [128,256)
+    const int m = q * 32 + lane;          // tile row = TMEM lane
+    const int cbase = ch * 128;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbase;
+    const int S = (MODE == 0) ? P.n_samples : 1;
+    const int HW = (MODE == 0) ? P.height * P.width : a.n_points;
+    const float* pk = a.packed;
+    uint32_t pd = 0;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int b = tile / a.tiles_per_image;
+      const int t_in = tile - b * a.tiles_per_image;
+      const int unit0 = t_in * a.rays_per_tile;
+      const int n_units = min(a.rays_per_tile, HW - unit0);
+      const int n_valid = n_units * S;
+      const size_t samp0 = ((size_t)b * HW + unit0) * S;
+      const float* film = a.in.film + (size_t)b * 9 * FILM_ROWS * SW;
+      const bool valid = m < n_valid;
+      const int r = valid ? m / S : 0, s = valid ? m - r * S : 0;
+
+      // ---- per-row geometry, recomputed by both column halves ----
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
+      if (MODE == 0) {
+        if (valid) {
+          const int ray = unit0 + r, py = ray / P.width, px = ray - py * P.width;
+          const float foc = a.in.focal[b], half = (float)P.res * 0.5f;
+          const float dx = __fdiv_rn(__fsub_rn(a.in.pix_x[px], half), foc);
+          const float dy = -__fdiv_rn(__fsub_rn(a.in.pix_y[py], half), foc);
+          const float dz = -1.f;
+          const float* c2w = a.in.cam_poses + (size_t)b * 12;
+          float rd[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            rd[c] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w[c * 4 + 0]), __fmul_rn(dy, c2w[c * 4 + 1])),
+                              __fmul_rn(dz, c2w[c * 4 + 2]));
+          if (P.flags & E3_RENDER_STATIC_VIEWDIRS) v0 = dx, v1 = dy, v2 = dz;
+          else v0 = rd[0], v1 = rd[1], v2 = rd[2];
+          const float vn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), __fmul_rn(v2, v2)));
+          v0 = __fdiv_rn(v0, vn), v1 = __fdiv_rn(v1, vn), v2 = __fdiv_rn(v2, vn);
+          const float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rd[0], rd[0]), __fmul_rn(rd[1], rd[1])),
+                                           __fmul_rn(rd[2], rd[2])));
+          const float o[3] = {c2w[3], c2w[7], c2w[11]};
+          const float nr = a.in.near[b], fr = a.in.far[b];
+          auto z_of = [&](int si) -> float {
+            if (a.in.z_jitter) return a.in.z_jitter[samp0 + r * S + si];
+            const float t = a.in.t_vals[si];
+            return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+          };
+          const float z = z_of(s);
+          float pw[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) pw[c] = __fadd_rn(o[c], __fmul_rn(rd[c], z));
+          x0 = __fmul_rn(pw[0], P.pts_scale), x1 = __fmul_rn(pw[1], P.pts_scale),
+          x2 = __fmul_rn(pw[2], P.pts_scale);
+          if (ch == 0) {
+            float dd;
+            if (s + 1 < S) dd = __fsub_rn(z_of(s + 1), z);
+            else if (P.flags & E3_RENDER_NO_FORCE_STOP) dd = (S > 1) ? __fsub_rn(z_of(1), z_of(0)) : 0.f;
+            else dd = 1e10f;
+            dd = __fmul_rn(dd, dn);
+            sm.z[m] = z;
+            sm.dist[m] = dd;
+            if (a.out.dists) a.out.dists[samp0 + m] = dd;
+            if (a.out.points) {
+              float* op = a.out.points + (samp0 + m) * 3;
+              op[0] = pw[0], op[1] = pw[1], op[2] = pw[2];
+            }
+            if (s == 0) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) sm.ray_o[c][r] = o[c], sm.ray_d[c][r] = rd[c];
+              const size_t ro = ((size_t)b * HW + ray) * 3;
+              if (a.out.rays_o) a.out.rays_o[ro] = o[0], a.out.rays_o[ro + 1] = o[1], a.out.rays_o[ro + 2] = o[2];
+              if (a.out.rays_d) a.out.rays_d[ro] = rd[0], a.out.rays_d[ro + 1] = rd[1], a.out.rays_d[ro + 2] = rd[2];
+              if (a.out.viewdirs) a.out.viewdirs[ro] = v0, a.out.viewdirs[ro + 1] = v1, a.out.viewdirs[ro + 2] = v2;
+            }
+          }
+        }
+      } else if (valid) {
+        const float* pp = a.points + (samp0 + m) * 3;
+        x0 = __fmul_rn(pp[0], P.pts_scale), x1 = __fmul_rn(pp[1], P.pts_scale),
+        x2 = __fmul_rn(pp[2], P.pts_scale);
+        if (a.pviewdirs) {
+          const float* vv = a.pviewdirs + (samp0 + m) * 3;
+          v0 = vv[0], v1 = vv[1], v2 = vv[2];
+        }
+      }
+
+      // publish the layer's A operand: generic-proxy stores -> visible to the async proxy (UMMA)
+      auto publish_a = [&]() {
+        fence_proxy_async();
+        tc::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.a_ready);
+      };
+
+      // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta') ----
+      {
+        const float* gam = film;
+        const float* betp = film + 2 * SW;
+#pragma unroll 1
+        for (int g8 = 0; g8 < 16; ++g8) {
+          const int n0 = cbase + g8 * 8;
+          float v[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const int n = n0 + j4 * 4;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + n));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + SW + n));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + 2 * SW + n));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(betp + n));
+            const float acc[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
+                                  fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
+            v[j4 * 4 + 0] = sin_accurate(fmaf(g.x, acc[0], be.x));
+            v[j4 * 4 + 1] = sin_accurate(fmaf(g.y, acc[1], be.y));
+            v[j4 * 4 + 2] = sin_accurate(fmaf(g.z, acc[2], be.z));
+            v[j4 * 4 + 3] = sin_accurate(fmaf(g.w, acc[3], be.w));
+          }
+          store_a8(sm, m, n0, v);
+        }
+        publish_a();
+      }
+
+      // ---- hidden layers 1..7: TMEM -> FiLM + sin -> next A operand ----
+      float sdf_acc = 0.f;
+      for (int l = 1; l < 8; ++l) {
+        mbar_wait(&sm.d_ready, pd);
+        pd ^= 1;
+        tc::fence_after_thread_sync();
+        const float* gam = film + (size_t)l * FILM_ROWS * SW;
+        const float* betp = gam + 2 * SW;
+        const bool last = (l == 7);
+        const float* la = nullptr;
+        const float* lb = nullptr;
+        if (MODE == 0 && last && a.in.local_alpha && valid) {
+          la = a.in.local_alpha + (samp0 + m) * SW;
+          lb = a.in.local_beta + (samp0 + m) * SW;
+        }
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          float acc[32];
+          tc::tmem_ld_32x32(trow + chunk * 32, acc);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int n0 = cbase + chunk * 32 + g8 * 8;
+            float v[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const int n = n0 + j4 * 4;
+              const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n));
+              const float4 be = __ldg(reinterpret_cast<const float4*>(betp + n));
+              v[j4 * 4 + 0] = sin_accurate(fmaf(g.x, acc[g8 * 8 + j4 * 4 + 0], be.x));
+              v[j4 * 4 + 1] = sin_accurate(fmaf(g.y, acc[g8 * 8 + j4 * 4 + 1], be.y));
+              v[j4 * 4 + 2] = sin_accurate(fmaf(g.z, acc[g8 * 8 + j4 * 4 + 2], be.z));
+              v[j4 * 4 + 3] = sin_accurate(fmaf(g.w, acc[g8 * 8 + j4 * 4 + 3], be.w));
+            }
+            if (last) {
+              // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
+#pragma unroll
+              for (int j4 = 0; j4 < 2; ++j4) {
+                const float4 ws = __ldg(reinterpret_cast<const float4*>(pk + OFF_WSIG + n0 + j4 * 4));
+                sdf_acc = fmaf(ws.x, v[j4 * 4 + 0], sdf_acc);
+                sdf_acc = fmaf(ws.y, v[j4 * 4 + 1], sdf_acc);
+                sdf_acc = fmaf(ws.z, v[j4 * 4 + 2], sdf_acc);
+                sdf_acc = fmaf(ws.w, v[j4 * 4 + 3], sdf_acc);
+              }
+              if (la) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  v[j] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + j], 1.f), v[j]), lb[n0 + j]);
+              }
+            }
+            if (!last || a.with_view) store_a8(sm, m, n0, v);
+          }
+        }
+        if (!last || a.with_view) publish_a();
+        else tc::fence_before_thread_sync();
+      }
+      sm.sdf_part[ch][m] = sdf_acc;
+      compute_sync();
+
+      // ---- sdf -> sigma -> alpha -> transmittance scan (overlaps the view-layer MMAs) ----
+      if (MODE == 0) {
+        if (ch == 0 && valid) {
+          const float sd = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
+          float al;
+          if (P.flags & E3_RENDER_NO_SDF) {
+            const float sp = (sd > 20.f) ? sd : log1pf(expf(sd));
+            al = 1.f - expf(-sp * sm.dist[m]);
+          } else {
+            const float beta = a.in.sigmoid_beta[0];
+            const float sigma = __fdiv_rn(sigmoid_acc(__fdiv_rn(-sd, beta)), beta);
+            al = 1.f - expf(-sigma * sm.dist[m]);
+          }
+          sm.alpha[m] = al;
+          if (a.out.sdf) a.out.sdf[samp0 + m] = sd;
+        }
+        compute_sync();
+        if (ct < n_units) {
+          const int rr = ct;
+          float T = 1.f, wsum = 0.f;
+          for (int si = 0; si < S; ++si) {
+            const int mm = rr * S + si;
+            const float al = sm.alpha[mm];
+            float w = __fmul_rn(al, T);
+            if ((P.flags & E3_RENDER_FORCE_BACKGROUND) && !(P.flags & E3_RENDER_NO_FORCE_STOP) && si == S - 1)
+              w = __fsub_rn(1.f, wsum);
+            sm.vis[mm] = T;
+            sm.wgt[mm] = w;
+            wsum = __fadd_rn(wsum, w);
+            T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, al), 1e-10f));
+          }
+          float depth = 0.f, xs = 0.f, ys = 0.f, zs = 0.f;
+          for (int si = 0; si < S; ++si) {
+            const int mm = rr * S + si;
+            const float w = sm.wgt[mm], z = sm.z[mm];
+            depth = fmaf(w, z, depth);
+            xs = fmaf(w, __fadd_rn(sm.ray_o[0][rr], __fmul_rn(sm.ray_d[0][rr], z)), xs);
+            ys = fmaf(w, __fadd_rn(sm.ray_o[1][rr], __fmul_rn(sm.ray_d[1][rr], z)), ys);
+            zs = fmaf(w, __fadd_rn(sm.ray_o[2][rr], __fmul_rn(sm.ray_d[2][rr], z)), zs);
+          }
+          const size_t pix = (size_t)b * HW + unit0 + rr;
+          if (a.out.depth) a.out.depth[pix] = depth;
+          if (a.out.mask) a.out.mask[pix] = (depth < P.mask_depth) ? 1.f : 0.f;
+          if (a.out.xyz) {
+            float* o = a.out.xyz + (size_t)b * 3 * HW + unit0 + rr;
+            o[0] = xs, o[HW] = ys, o[2 * (size_t)HW] = zs;
+          }
+        }
+        compute_sync();
+        if (ch == 0 && valid) {
+          if (a.out.hit_prob) a.out.hit_prob[samp0 + m] = sm.wgt[m];
+          if (a.out.visibility) a.out.visibility[samp0 + m] = sm.vis[m];
+        }
+      } else {
+        if (ch == 0 && valid) a.p_sdf[samp0 + m] = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
+      }
+
+      if (a.with_view) {
+        // ---- view layer epilogue: + W_dir*viewdir, FiLM, sin; rgb head; weighted feature sum ----
+        mbar_wait(&sm.d_ready, pd);
+        pd ^= 1;
+        tc::fence_after_thread_sync();
+        const float* gam = film + (size_t)8 * FILM_ROWS * SW;
+        const float* betp = gam + 2 * SW;
+        const float wrow = (MODE == 0 && valid) ? sm.wgt[m] : 0.f;
+        float* fbuf = reinterpret_cast<float*>(sm.a_hi);  // [256][128] fp32 over a_hi + a_lo
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          float acc[32];
+          tc::tmem_ld_32x32(trow + chunk * 32, acc);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int n = cbase + chunk * 32 + j4 * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(betp + n));
+            const float4 d0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + n));
+            const float4 d1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + SW + n));
+            const float4 d2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + 2 * SW + n));
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + n));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + SW + n));
+            const float4 r2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + 2 * SW + n));
+            const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
+            const float e0[4] = {d0.x, d0.y, d0.z, d0.w}, e1[4] = {d1.x, d1.y, d1.z, d1.w},
+                        e2[4] = {d2.x, d2.y, d2.z, d2.w};
+            const float q0[4] = {r0.x, r0.y, r0.z, r0.w}, q1[4] = {r1.x, r1.y, r1.z, r1.w},
+                        q2[4] = {r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float pre = acc[j4 * 4 + j];
+              pre = fmaf(e0[j], v0, pre);
+              pre = fmaf(e1[j], v1, pre);
+              pre = fmaf(e2[j], v2, pre);
+              const float f = sin_accurate(fmaf(gg[j], pre, bb[j]));
+              c0 = fmaf(q0[j], f, c0);
+              c1 = fmaf(q1[j], f, c1);
+              c2 = fmaf(q2[j], f, c2);
+              acc[j4 * 4 + j] = f;
+            }
+          }
+          if (MODE == 1) {
+            if (a.p_feat && valid) {
+              float4* dst = reinterpret_cast<float4*>(a.p_feat + (samp0 + m) * SW + cbase + chunk * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+          }
+          // stage w*f for the per-ray sum (all view-layer MMAs have completed — d_ready — so the
+          // A-operand region is free; each thread owns its (n, m) slots, no cross-thread hazard)
+          if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = cbase + chunk * 32 + j;
+              fbuf[n * TCM + (m ^ (n & 31))] = wrow * acc[j];
+            }
+          }
+        }
+        sm.rgb_part[ch][0][m] = c0;
+        sm.rgb_part[ch][1][m] = c1;
+        sm.rgb_part[ch][2][m] = c2;
+        tc::fence_before_thread_sync();
+        compute_sync();
+
+        if (MODE == 0) {
+          if (a.out.raw_rgb && ch == 0 && valid) {
+            float* o = a.out.raw_rgb + (samp0 + m) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              o[c] = sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m] + pk[OFF_HEADB + 1 + c];
+          }
+          if (a.out.thumb_rgb && ct < 3 * n_units) {
+            const int c = ct / n_units, rr = ct - c * n_units;
+            float accum = 0.f;
+            for (int si = 0; si < S; ++si) {
+              const int mm = rr * S + si;
+              const float raw = sm.rgb_part[0][c][mm] + sm.rgb_part[1][c][mm] + pk[OFF_HEADB + 1 + c];
+              accum = fmaf(sm.wgt[mm], sigmoid_acc(raw), accum);
+            }
+            a.out.thumb_rgb[((size_t)b * 3 + c) * HW + unit0 + rr] = -1.f + 2.f * accum;
+          }
+          if (a.out.features) {
+            const int n = ct;  // one output channel per compute thread
+            const float* row = fbuf + n * TCM;
+            const int sw = n & 31;
+            float* o = a.out.features + ((size_t)b * SW + n) * HW + unit0;
+            for (int rr = 0; rr < n_units; ++rr) {
+              float accum = 0.f;
+              for (int si = 0; si < S; ++si) accum += row[(rr * S + si) ^ sw];
+              o[rr] = accum;
+            }
+          }
+        } else if (a.p_rgb && ch == 0 && valid) {
+          float* o = a.p_rgb + (samp0 + m) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            o[c] = sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m] + pk[OFF_HEADB + 1 + c];
+        }
+      }
+      compute_sync();  // shared memory is reused by the next tile
+    }
+  }
+
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+}
+
+int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream) {
+  static thread_local bool attr_set[2] = {false, false};
+  const int smem_bytes = (int)sizeof(SmemTC) + 1024;
+  const void* fn = (mode == 0) ? (const void*)siren_render_tc_kernel<0> : (const void*)siren_render_tc_kernel<1>;
+  if (!attr_set[mode]) {
+    E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set[mode] = true;
+  }
+  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  if (grid <= 0) return E3_OK;
+  if (mode == 0)
+    siren_render_tc_kernel<0><<<grid, TC_NTHREADS, smem_bytes, stream>>>(a);
+  else
+    siren_render_tc_kernel<1><<<grid, TC_NTHREADS, smem_bytes, stream>>>(a);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+}  // namespace e3

@@ -44,6 +44,7 @@ RENDER_STATIC_VIEWDIRS = 1
 RENDER_FORCE_BACKGROUND = 2
 RENDER_NO_FORCE_STOP = 4
 RENDER_NO_SDF = 8
+RENDER_FP32_CUDA_CORES = 16
 CONV_AUTO, CONV_FP32_CUDA_CORES, CONV_TENSOR_CORES = 0, 1, 2
 
 _PROTOTYPES = {
@@ -54,7 +55,8 @@ _PROTOTYPES = {
     "e3_film_fwd": (c_int, [_fp, _fp, c_int, c_int, _fp, _fp]),
     "e3_render_fwd": (c_int, [_fp, POINTER(RenderParams), POINTER(RenderInputs),
                               POINTER(RenderOutputs), _fp]),
-    "e3_siren_points_fwd": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, _fp]),
+    "e3_siren_points_fwd": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, c_uint32,
+                                    _fp]),
     "e3_fused_bias_act": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_int64, c_int64, c_int, c_int,
                                   c_float, c_float, _fp]),
     "e3_upfirdn2d": (c_int, [_fp, _fp, _fp] + [c_int] * 14 + [_fp]),

@@ -251,6 +251,9 @@ class VolumeFeatureRenderer(nn.Module):
         self.register_buffer("B_MIN", -torch.Tensor([r] * 3), persistent=False)
         self.local_batch = None
         self.sample_mode = False
+        # arithmetic of the 256x256 hidden layers: "tensor_cores" (tcgen05 split-bf16, default) or
+        # "fp32" (exact-fp32 FFMA kernel) — include/e3dge_b200.h E3_RENDER_FP32_CUDA_CORES
+        self.backend = "tensor_cores"
         self._packed = _PackedSiren()
         self._last_names = None
 
@@ -271,10 +274,13 @@ class VolumeFeatureRenderer(nn.Module):
             b, spi = styles.shape[0], 9
         else:
             raise RuntimeError(f"styles must be [B,256] (w) or [B,9,256] (w+), got {tuple(styles.shape)}")
-        film = torch.empty(b, 9, 2, 256, device=styles.device, dtype=torch.float32)
+        film = torch.empty(b, 9, 3, 256, device=styles.device, dtype=torch.float32)
         _lib.check(lib.e3_film_fwd(_lib.ptr(self.packed_weights()), _lib.ptr(styles), b, spi,
                                    _lib.ptr(film), _lib.cur_stream()), "e3_film_fwd")
         return film
+
+    def _point_flags(self):
+        return _lib.RENDER_FP32_CUDA_CORES if self.backend == "fp32" else 0
 
     def _flags(self, no_force_stop=False):
         f = 0
@@ -286,6 +292,8 @@ class VolumeFeatureRenderer(nn.Module):
             f |= _lib.RENDER_NO_FORCE_STOP
         if not self.with_sdf:
             f |= _lib.RENDER_NO_SDF
+        if self.backend == "fp32":
+            f |= _lib.RENDER_FP32_CUDA_CORES
         return f
 
     def _render_raw(self, styles, cam_poses, focal, near, far, z_jitter=None, local_mod=None,
@@ -400,7 +408,8 @@ class VolumeFeatureRenderer(nn.Module):
         _lib.check(lib.e3_siren_points_fwd(_lib.ptr(self.packed_weights()), _lib.ptr(film),
                                            _lib.ptr(pts), _lib.ptr(vd), B, N,
                                            float(self.grid_warper.scale_factor), _lib.ptr(sdf),
-                                           _lib.ptr(rgb), _lib.ptr(feat), _lib.cur_stream()),
+                                           _lib.ptr(rgb), _lib.ptr(feat), self._point_flags(),
+                                           _lib.cur_stream()),
                    "e3_siren_points_fwd")
         if return_sdf_only:
             return sdf.reshape(*shp[:-1], 1)
@@ -417,7 +426,8 @@ class VolumeFeatureRenderer(nn.Module):
         _lib.check(lib.e3_siren_points_fwd(_lib.ptr(self.packed_weights()), _lib.ptr(film),
                                            _lib.ptr(pts), None, B, N,
                                            float(self.grid_warper.scale_factor), _lib.ptr(sdf), None,
-                                           None, _lib.cur_stream()), "e3_siren_points_fwd")
+                                           None, self._point_flags(), _lib.cur_stream()),
+                   "e3_siren_points_fwd")
         return sdf.unsqueeze(-1)
 
     def sample_uniform_grid(self, batch_size, num_sample_inout, device, styles):

@@ -69,7 +69,8 @@ int e3_siren_pack(const e3_siren_weights* w, void* packed, void* stream);
  * (FiLMSiren.gamma/.beta, volume_renderer.py:107-114,119-120).
  * styles [batch, styles_per_image, 256]; styles_per_image is 9 (w+: layer i uses style i,
  * the view layer uses the last one, volume_renderer.py:176-178,226-227) or 1 (w).
- * film [batch, 9, 2, 256] (gamma row then beta row per layer). */
+ * film [batch, 9, 3, 256]: per layer the rows gamma, beta, and beta' = gamma*bias + beta
+ * (the layer bias folded in, read by the tensor-core renderer). */
 int e3_film_fwd(const void* packed, const float* styles, int batch, int styles_per_image,
                 float* film, void* stream);
 
@@ -78,13 +79,18 @@ int e3_film_fwd(const void* packed, const float* styles, int batch, int styles_p
 #define E3_RENDER_FORCE_BACKGROUND 2u /* rendering.force_background (:884-886) */
 #define E3_RENDER_NO_FORCE_STOP 4u    /* volume_integration(no_force_stop=True) (:830-836) */
 #define E3_RENDER_NO_SDF 8u           /* rendering.no_sdf: softplus density (:862-867) */
+/* arithmetic of the eight 256x256 hidden-layer contractions (not a reference option):
+ * default = tcgen05 tensor cores with split-bf16 operands (h_hi*W_hi + h_lo*W_hi + h_hi*W_lo,
+ * fp32 accumulation in TMEM; ~1e-4 of the fp32 reference end to end); this flag selects the
+ * exact-fp32 FFMA kernel instead (~3e-5, the fp32 noise floor), at ~1/6 of the speed. */
+#define E3_RENDER_FP32_CUDA_CORES 16u
 
 typedef struct e3_render_params {
   int32_t batch;
   int32_t height;    /* rays per column  = out_im_res * spatial_ss */
   int32_t width;     /* rays per row */
   int32_t res;       /* out_im_res: principal point = res/2 (volume_renderer.py:773-774) */
-  int32_t n_samples; /* rendering.N_samples, <= 96 */
+  int32_t n_samples; /* rendering.N_samples, <= 128 (<= 96 with E3_RENDER_FP32_CUDA_CORES) */
   uint32_t flags;
   float pts_scale;   /* 1/dist_radius, UniformBoxWarp (:23-30,720) */
   float mask_depth;  /* 1.08 (:910) */
@@ -101,7 +107,7 @@ typedef struct e3_render_inputs {
   const float* t_vals;       /* [n_samples] the `t_vals` buffer (:690-698) */
   const float* z_jitter;     /* NULL, or [B,H,W,S] replacement z_vals (perturb > 0, :1213-1228) */
   const float* sigmoid_beta; /* [1] learned (:662-663) */
-  const float* film;         /* [B,9,2,256] from e3_film_fwd */
+  const float* film;         /* [B,9,3,256] from e3_film_fwd */
   const float* local_alpha;  /* NULL or [B,H,W,S,256]: (alpha+1)*h + beta before the view */
   const float* local_beta;   /*                        layer (:217-220) */
 } e3_render_inputs;
@@ -138,10 +144,11 @@ int e3_render_fwd(const void* packed, const e3_render_params* p, const e3_render
  * volume_renderer.py:955-957, 996-998, 1935-1943).
  * points [B,N,3]; viewdirs NULL (= zeros, geometry queries) or [B,N,3];
  * sdf [B,N]; raw_rgb NULL or [B,N,3]; feat NULL or [B,N,256].  When raw_rgb and feat are
- * both NULL the view layer is skipped (return_sdf_only, :1125-1126). */
+ * both NULL the view layer is skipped (return_sdf_only, :1125-1126).
+ * flags: 0 or E3_RENDER_FP32_CUDA_CORES. */
 int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
                         const float* viewdirs, int batch, int n_points, float pts_scale,
-                        float* sdf, float* raw_rgb, float* feat, void* stream);
+                        float* sdf, float* raw_rgb, float* feat, uint32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * StyleGAN2 ops — same semantics and argument order as the reference's extension ABI.

@@ -316,3 +316,51 @@ def test_decoder_backends_agree_at_full_size():
         _set_backend(G, "fp32")
         b, _ = G.decoder(feats, [inp["w_dec"]], input_is_latent=True, randomize_noise=False)
     assert rel_linf(a.cpu(), b.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small_wplus", "small_s18_rayd_viewdirs", "small_sharp_w"])
+def test_renderer_exact_fp32_backend_vs_reference_fixture(name):
+    """The FFMA kernel (E3_RENDER_FP32_CUDA_CORES) stays covered now that tensor cores are the default."""
+    gold, cfg = load_golden(name)
+    G, sd = _build(cfg["size"], cfg["res"], cfg["seed"], cfg["variant"], cfg["n_samples"], **cfg["ropt"])
+    G.renderer.backend = "fp32"
+    d = _cuda(P.make_inputs(cfg["seed"], cfg["batch"], decoder_layout(cfg["size"], cfg["res"]),
+                            cfg["res"], wplus=cfg["wplus"]))
+    with torch.no_grad():
+        out = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
+    for k in ("features", "gen_thumb_imgs", "sdf", "hit_prob", "xyz", "depth", "dists", "points"):
+        assert rel_linf(out[k].cpu(), gold[k]) < 2e-4, k   # fp32 FFMA sits at the fp32 noise floor
+
+
+@pytest.mark.parametrize("backend,n_samples", [("tensor_cores", 1), ("tensor_cores", 7),
+                                               ("tensor_cores", 48), ("tensor_cores", 128),
+                                               ("fp32", 5), ("fp32", 96)])
+def test_renderer_sample_counts_vs_oracle(backend, n_samples):
+    """Tiles hold floor(tile/S) whole rays: exercise S that do not divide the tile, S = tile, S = 1."""
+    size, res, seed = 64, 8, 400 + n_samples
+    G, sd = _build(size, res, seed, "sharp", n_samples=n_samples, full_pipeline=False)
+    G.renderer.backend = backend
+    inp = P.make_inputs(seed, 2, 1, res)
+    d = _cuda(inp)
+    with torch.no_grad():
+        out = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
+        ref = O.renderer_forward(sd, inp["cam_poses"], inp["focal"], inp["near"], inp["far"],
+                                 inp["w"], res=res, n_samples=n_samples)
+    for k in ("features", "gen_thumb_imgs", "sdf", "hit_prob", "xyz", "depth"):
+        assert rel_linf(out[k].cpu(), ref[k]) < TOL, (k, backend, n_samples)
+
+
+def test_renderer_backends_agree_at_full_size_and_too_many_samples_is_refused():
+    size, res, seed = 256, 64, 77
+    G, sd = _build(size, res, seed, "sharp")
+    d = _cuda(P.make_inputs(seed, 2, decoder_layout(size, res), res))
+    outs = {}
+    for backend in ("tensor_cores", "fp32"):
+        G.renderer.backend = backend
+        with torch.no_grad():
+            outs[backend] = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
+    for k in ("features", "gen_thumb_imgs", "sdf", "hit_prob", "xyz"):
+        assert rel_linf(outs["tensor_cores"][k].cpu(), outs["fp32"][k].cpu()) < TOL, k
+    G2, _ = _build(64, 8, 1, "default", n_samples=129, full_pipeline=False)
+    with pytest.raises(RuntimeError, match="n_samples"):
+        G2.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
