@@ -266,6 +266,14 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         if (lane == 0) mbar_arrive(&sm.a_ready);
       };
 
+      // rendering.return_feats: hidden states after 0-based layers 0,2,4,6 (volume_renderer.py:179-180)
+      auto store_tap = [&](int tap, int n0, const float* v) {
+        float4* dst = reinterpret_cast<float4*>(
+            a.out.feats_taps + ((size_t)tap * P.batch * HW * S + samp0 + m) * SW + n0);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      };
+
       // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta') ----
       {
         const float* gam = film;
@@ -290,6 +298,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
             v[j4 * 4 + 3] = sin_accurate(fmaf(g.w, acc[3], be.w));
           }
           store_a8(sm, m, n0, v);
+          if (MODE == 0 && a.out.feats_taps && valid) store_tap(0, n0, v);
         }
         publish_a();
       }
@@ -343,6 +352,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
                   v[j] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + j], 1.f), v[j]), lb[n0 + j]);
               }
             }
+            if (MODE == 0 && a.out.feats_taps && (l & 1) == 0 && valid) store_tap(l >> 1, n0, v);
             if (!last || a.with_view) store_a8(sm, m, n0, v);
           }
         }
