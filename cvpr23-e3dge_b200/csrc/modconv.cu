@@ -235,63 +235,89 @@ struct Col2imArgs {
   const float* act_bias;  // NULL: bare modulated conv (d * blur(convT)), no noise / bias / act
 };
 
+// One thread = a 2x2 output block (rows 2y,2y+1; cols 2x,2x+1) x 4 channels.  Along one axis the
+// pair of outputs (2y, 2y+1) depends on input rows y-1, y, y+1 through 7 (row, tap) terms:
+//   out[2y]   = .25 G[y-1,k1] + .75 G[y-1,k2] + .75 G[y,k0] + .75 G[y,k1] + .25 G[y,k2] + .25 G[y+1,k0]
+//   out[2y+1] = .25 G[y-1,k2] + .25 G[y,k0] + .75 G[y,k1] + .75 G[y,k2] + .75 G[y+1,k0] + .25 G[y+1,k1]
+// (transposed-conv scatter P = 2*iy + k, then blur taps [1,3,3,1]/4 at P = Y-1..Y+2), so the block
+// reads 7x7 = 49 G vectors instead of 4 x 36.
+__device__ __forceinline__ float c2i_coef(int phase, int d, int k) {
+  // d = input offset + 1 (0..2), k = conv tap (0..2)
+  const float c[2][3][3] = {{{0.f, .25f, .75f}, {.75f, .75f, .25f}, {.25f, 0.f, 0.f}},
+                            {{0.f, 0.f, .25f}, {.25f, .75f, .75f}, {.75f, .25f, 0.f}}};
+  return c[phase][d][k];
+}
+
 __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_constant__ Col2imArgs a) {
   const int c4n = a.cout >> 2;
-  const int OH = 2 * a.H, OW = 2 * a.W;
-  const int64_t total = (int64_t)a.B * OH * OW * c4n;
+  const int OW = 2 * a.W, OH = 2 * a.H;
+  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
   const bool linear = a.act_bias == nullptr;
   const float nw = linear ? 0.f : a.noise_w[0];
-  const float kb[4] = {0.25f, 0.75f, 0.75f, 0.25f};
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int o = (int)(idx % c4n) * 4;
     int64_t t = idx / c4n;
-    const int X = (int)(t % OW);
-    t /= OW;
-    const int Y = (int)(t % OH);
-    const int b = (int)(t / OH);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int x = (int)(t % a.W);
+    t /= a.W;
+    const int y = (int)(t % a.H);
+    const int b = (int)(t / a.H);
+    float4 acc[2][2];
 #pragma unroll
-    for (int ay = 0; ay < 4; ++ay) {
-      const int P = Y + ay - 1;
-      if (P < 0 || P > OH) continue;
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) acc[py][px] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = y + dy - 1;
+      if (iy < 0 || iy >= a.H) continue;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        const int ry = P - ky;
-        if (ry < 0 || (ry & 1)) continue;
-        const int iy = ry >> 1;
-        if (iy >= a.H) continue;
+        const float cy0 = c2i_coef(0, dy, ky), cy1 = c2i_coef(1, dy, ky);
+        if (cy0 == 0.f && cy1 == 0.f) continue;
 #pragma unroll
-        for (int ax = 0; ax < 4; ++ax) {
-          const int Q = X + ax - 1;
-          if (Q < 0 || Q > OW) continue;
-          const float wgt = kb[ay] * kb[ax];
+        for (int dx = 0; dx < 3; ++dx) {
+          const int ix = x + dx - 1;
+          if (ix < 0 || ix >= a.W) continue;
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const int rx = Q - kx;
-            if (rx < 0 || (rx & 1)) continue;
-            const int ix = rx >> 1;
-            if (ix >= a.W) continue;
+            const float cx0 = c2i_coef(0, dx, kx), cx1 = c2i_coef(1, dx, kx);
+            if (cx0 == 0.f && cx1 == 0.f) continue;
             const float4 gv = *reinterpret_cast<const float4*>(
                 a.g + ((((size_t)b * a.H + iy) * a.W + ix) * 9 + ky * 3 + kx) * a.cout + o);
-            acc.x = fmaf(wgt, gv.x, acc.x), acc.y = fmaf(wgt, gv.y, acc.y);
-            acc.z = fmaf(wgt, gv.z, acc.z), acc.w = fmaf(wgt, gv.w, acc.w);
+            const float w00 = cy0 * cx0, w01 = cy0 * cx1, w10 = cy1 * cx0, w11 = cy1 * cx1;
+            if (w00 != 0.f) acc[0][0].x = fmaf(w00, gv.x, acc[0][0].x), acc[0][0].y = fmaf(w00, gv.y, acc[0][0].y),
+                            acc[0][0].z = fmaf(w00, gv.z, acc[0][0].z), acc[0][0].w = fmaf(w00, gv.w, acc[0][0].w);
+            if (w01 != 0.f) acc[0][1].x = fmaf(w01, gv.x, acc[0][1].x), acc[0][1].y = fmaf(w01, gv.y, acc[0][1].y),
+                            acc[0][1].z = fmaf(w01, gv.z, acc[0][1].z), acc[0][1].w = fmaf(w01, gv.w, acc[0][1].w);
+            if (w10 != 0.f) acc[1][0].x = fmaf(w10, gv.x, acc[1][0].x), acc[1][0].y = fmaf(w10, gv.y, acc[1][0].y),
+                            acc[1][0].z = fmaf(w10, gv.z, acc[1][0].z), acc[1][0].w = fmaf(w10, gv.w, acc[1][0].w);
+            if (w11 != 0.f) acc[1][1].x = fmaf(w11, gv.x, acc[1][1].x), acc[1][1].y = fmaf(w11, gv.y, acc[1][1].y),
+                            acc[1][1].z = fmaf(w11, gv.z, acc[1][1].z), acc[1][1].w = fmaf(w11, gv.w, acc[1][1].w);
           }
         }
       }
     }
     const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);
-    float v[4] = {acc.x * dv.x, acc.y * dv.y, acc.z * dv.z, acc.w * dv.w};
-    if (!linear) {
-      const float nz = nw * a.noise[(size_t)b * a.noise_bstride + (size_t)Y * OW + X];
-      const float4 bv = *reinterpret_cast<const float4*>(a.act_bias + o);
-      v[0] = fmaf(acc.x, dv.x, nz) + bv.x, v[1] = fmaf(acc.y, dv.y, nz) + bv.y;
-      v[2] = fmaf(acc.z, dv.z, nz) + bv.z, v[3] = fmaf(acc.w, dv.w, nz) + bv.w;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!linear) bv = *reinterpret_cast<const float4*>(a.act_bias + o);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = (v[q] > 0.f ? v[q] : 0.2f * v[q]) * kSqrt2;
-    }
-    *reinterpret_cast<float4*>(a.y + (((size_t)b * OH + Y) * OW + X) * a.cout + o) =
-        make_float4(v[0], v[1], v[2], v[3]);
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int Y = 2 * y + py, X = 2 * x + px;
+        const float4 s4 = acc[py][px];
+        float v[4] = {s4.x * dv.x, s4.y * dv.y, s4.z * dv.z, s4.w * dv.w};
+        if (!linear) {
+          const float nz = nw * a.noise[(size_t)b * a.noise_bstride + (size_t)Y * OW + X];
+          v[0] = fmaf(s4.x, dv.x, nz) + bv.x, v[1] = fmaf(s4.y, dv.y, nz) + bv.y;
+          v[2] = fmaf(s4.z, dv.z, nz) + bv.z, v[3] = fmaf(s4.w, dv.w, nz) + bv.w;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) v[qq] = (v[qq] > 0.f ? v[qq] : 0.2f * v[qq]) * kSqrt2;
+        }
+        *reinterpret_cast<float4*>(a.y + (((size_t)b * OH + Y) * OW + X) * a.cout + o) =
+            make_float4(v[0], v[1], v[2], v[3]);
+      }
   }
 }
 
@@ -361,23 +387,25 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __grid_constant__ ToRg
 }
 
 // ---- image-parallel inversion record ----------------------------------------
+// blockIdx.x = image, blockIdx.y = slice of the image: every slice copies its share of the latents
+// and adds its partial squared / absolute error sums to the record's two metric slots (pre-zeroed).
 __global__ void __launch_bounds__(256) pack_record_kernel(const float* __restrict__ w_plus,
                                                           const float* __restrict__ w_dec,
                                                           int n_latent, const float* __restrict__ image,
                                                           const float* __restrict__ target,
                                                           int64_t image_numel,
                                                           float* __restrict__ record) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
   const int rec_len = 2304 + n_latent * 512 + 2;
   float* rec = record + (size_t)b * rec_len;
-  for (int i = threadIdx.x; i < 2304; i += blockDim.x) rec[i] = w_plus[(size_t)b * 2304 + i];
-  for (int i = threadIdx.x; i < n_latent * 512; i += blockDim.x)
-    rec[2304 + i] = w_dec[(size_t)b * n_latent * 512 + i];
+  const int tid = part * blockDim.x + threadIdx.x, nthr = parts * blockDim.x;
+  for (int i = tid; i < 2304; i += nthr) rec[i] = w_plus[(size_t)b * 2304 + i];
+  for (int i = tid; i < n_latent * 512; i += nthr) rec[2304 + i] = w_dec[(size_t)b * n_latent * 512 + i];
   float se = 0.f, ae = 0.f;
   if (image && target) {
     const float* im = image + (size_t)b * image_numel;
     const float* tg = target + (size_t)b * image_numel;
-    for (int64_t i = threadIdx.x; i < image_numel; i += blockDim.x) {
+    for (int64_t i = tid; i < image_numel; i += nthr) {
       const float dlt = im[i] - tg[i];
       se = fmaf(dlt, dlt, se);
       ae += fabsf(dlt);
@@ -391,8 +419,8 @@ __global__ void __launch_bounds__(256) pack_record_kernel(const float* __restric
   if (threadIdx.x == 0) {
     float s2 = 0.f, a2 = 0.f;
     for (int i = 0; i < 8; ++i) s2 += red[0][i], a2 += red[1][i];
-    rec[rec_len - 2] = s2 / (float)image_numel;
-    rec[rec_len - 1] = a2 / (float)image_numel;
+    atomicAdd(&rec[rec_len - 2], s2 / (float)image_numel);
+    atomicAdd(&rec[rec_len - 1], a2 / (float)image_numel);
   }
 }
 
@@ -541,7 +569,7 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
   c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
   c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;
   c.act_bias = act_bias;
-  const int64_t total = (int64_t)batch * 4 * h * w * (cout / 4);
+  const int64_t total = (int64_t)batch * h * w * (cout / 4);  // one thread per 2x2 output block x 4 ch
   col2im_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(c);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
@@ -573,8 +601,11 @@ extern "C" int e3_pack_inversion_record(const float* w_plus, const float* w_dec,
   E3_REQUIRE((image == nullptr) == (target == nullptr), E3_ERR_BAD_ARG,
              "e3_pack_inversion_record: image and target come together");
   if (batch == 0) return E3_OK;
-  pack_record_kernel<<<batch, 256, 0, as_stream(stream)>>>(w_plus, w_dec, n_latent, image, target,
-                                                          image_numel > 0 ? image_numel : 1, record);
+  const int rec_len = 2304 + n_latent * 512 + 2;
+  E3_CUDA(cudaMemsetAsync(record, 0, (size_t)batch * rec_len * sizeof(float), as_stream(stream)));
+  const int parts = image ? 32 : 1;
+  pack_record_kernel<<<dim3(batch, parts), 256, 0, as_stream(stream)>>>(
+      w_plus, w_dec, n_latent, image, target, image_numel > 0 ? image_numel : 1, record);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
 }

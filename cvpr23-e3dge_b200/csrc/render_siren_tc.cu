@@ -9,21 +9,28 @@
 //   * the hidden state lives in shared memory as the UMMA A operand: bf16 hi + bf16 lo
 //     (h = hi + lo to 2^-17), K-major SWIZZLE_128B, 4 k-blocks x 16 KB each — written in place
 //     by the epilogue of the previous layer;
-//   * per layer D[128x256] (fp32, 256 TMEM columns) = h_hi*W_hi^T + h_lo*W_hi^T + h_hi*W_lo^T:
+//   * per layer D[128x256] (fp32 in TMEM) = h_hi*W_hi^T + h_lo*W_hi^T + h_hi*W_lo^T:
 //     96 tcgen05.mma 128x128x16 issued by one thread; the three-product split keeps the result
 //     fp32-faithful (measured 5e-5..1.5e-4 end to end vs 2..5e-2 for plain bf16 operands; the
 //     parity bar is 1e-3);
 //   * weights: 2 MB of pre-split, pre-swizzled bf16 tiles streamed from L2 by cp.async.bulk
 //     (TMA) through a 4 x 16 KB full/empty mbarrier ring, one 128(n) x 64(k) tile per stage;
-//   * 8 epilogue warps (each TMEM lane quarter twice, half the columns each): tcgen05.ld ->
-//     FiLM (bias folded into beta') -> accurate sin -> hi/lo split -> swizzled st.shared of the
-//     next layer's A operand; layer 0 (K = 3), the sdf / rgb heads, the view-direction rank-3
-//     update, the transmittance scan and the weighted feature sum stay on the CUDA cores.
+//   * 8 epilogue warps: tcgen05.ld -> FiLM (bias folded into beta', table in shared memory) ->
+//     accurate sin -> hi/lo split -> swizzled st.shared of the next layer's A operand; layer 0
+//     (K = 3), the sdf / rgb heads, the view-direction rank-3 update, the transmittance scan and
+//     the weighted feature sum stay on the CUDA cores.
+//
+// Layer pipelining.  Layer l+1 contracts over ALL outputs of layer l, but k-block j of that
+// contraction only needs output channels [64j, 64j+64).  The epilogue therefore walks a layer in
+// four 64-channel blocks and publishes each one (a_ready[j]); the MMA warp starts layer l+1's
+// k-block j as soon as it lands, accumulating into the OTHER half of TMEM (512 columns = two
+// 128x256 fp32 accumulators, ping-pong by layer parity).  Three quarters of a layer's MMA time
+// hide under the epilogue of the previous layer; overwriting the A operand in place is safe
+// because layer l's MMAs have all completed (d_ready) before its epilogue starts.
 //
 // Warp roles: warp 0 = TMA weight producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 =
-// compute.  MMA and epilogue of one tile are serialised by the layer-to-layer data dependence
-// (layer l+1 contracts over ALL outputs of layer l); the sdf->alpha->scan work of a tile
-// overlaps with the view-layer MMAs.
+// compute (TMEM lane quarter = warp % 4; the two warps of a quarter take 32 columns each of a
+// 64-channel block).  The sdf->alpha->scan work of a tile overlaps with the view-layer MMAs.
 #include <cuda_bf16.h>
 
 #include "render_siren.cuh"
@@ -43,12 +50,15 @@ struct SmemTC {
   uint8_t a_hi[A_BYTES];  // also the fp32 [256][128] composite buffer together with a_lo
   uint8_t a_lo[A_BYTES];
   uint8_t ring[TC_RING * TC_TILE_BYTES];
+  float film[9][2][SW];   // gamma, beta' = gamma*bias + beta of the current image
+  float w0[3][SW];        // layer-0 weights, natural channel order
+  float wsig[SW];
   float z[TCM], dist[TCM], alpha[TCM], wgt[TCM], vis[TCM];
   float sdf_part[2][TCM];
   float rgb_part[2][3][TCM];
   float ray_o[3][TCM], ray_d[3][TCM];
   uint64_t full[TC_RING], empty[TC_RING];
-  uint64_t a_ready, d_ready;
+  uint64_t a_ready[4], d_ready;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(SmemTC) + 1024 <= 227 * 1024, "shared memory budget");
@@ -92,11 +102,14 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
-    mbar_init(&sm.a_ready, TC_COMPUTE_WARPS);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], TC_COMPUTE_WARPS);
     mbar_init(&sm.d_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 256);
+  for (int i = tid; i < 3 * SW; i += TC_NTHREADS) sm.w0[0][i] = a.packed[OFF_W0N + i];
+  for (int i = tid; i < SW; i += TC_NTHREADS) sm.wsig[i] = a.packed[OFF_WSIG + i];
+  if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
@@ -131,11 +144,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
       uint32_t stage = 0, phase = 0, pa = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
-        for (int l = 0; l < gemm_layers; ++l) {
-          mbar_wait(&sm.a_ready, pa);  // this layer's A operand is in shared memory
-          pa ^= 1;
-          tc::fence_after_thread_sync();
+        for (int l = 0; l < gemm_layers; ++l) {  // l-th GEMM of the tile = reference layer l+1
+          const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256;
           for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&sm.a_ready[kb], pa);  // k-block kb of this layer's A operand is published
+            tc::fence_after_thread_sync();
             const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
             const uint64_t dAl = tc::make_smem_desc_sw128(a_lo0 + kb * A_KBLOCK_BYTES);
 #pragma unroll
@@ -144,7 +157,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
               mbar_wait(&sm.full[stage], phase);
               tc::fence_after_thread_sync();
               const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
-              const uint32_t d = tmem_base + nh * 128;
+              const uint32_t d = dcol + nh * 128;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t bk = tc::advance_desc_k(dB, ks);
@@ -162,6 +175,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
               }
             }
           }
+          pa ^= 1;  // each a_ready[kb] completes exactly once per layer
           tc::mma_commit(&sm.d_ready);
         }
       }
@@ -171,14 +185,22 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
     const e3_render_params& P = a.p;
     const int ct = tid - 64;              // 0..255
     const int q = warp & 3;               // TMEM lane quarter this warp may read
-    const int ch = (warp - 2) >> 2;       // column half: 0 -> channels [0,128), 1 -> [128,256)
+    const int hw = (warp - 2) >> 2;       // which 32-column half of each 64-channel block
     const int m = q * 32 + lane;          // tile row = TMEM lane
-    const int cbase = ch * 128;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + cbase;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + hw * 32;
     const int S = (MODE == 0) ? P.n_samples : 1;
     const int HW = (MODE == 0) ? P.height * P.width : a.n_points;
     const float* pk = a.packed;
     uint32_t pd = 0;
+    int cur_b = -1;
+
+    // publish k-block j of the next A operand: generic-proxy stores -> async proxy (UMMA)
+    auto publish = [&](int j) {
+      fence_proxy_async();
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.a_ready[j]);
+    };
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_image;
@@ -187,9 +209,17 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       const int n_units = min(a.rays_per_tile, HW - unit0);
       const int n_valid = n_units * S;
       const size_t samp0 = ((size_t)b * HW + unit0) * S;
-      const float* film = a.in.film + (size_t)b * 9 * FILM_ROWS * SW;
       const bool valid = m < n_valid;
       const int r = valid ? m / S : 0, s = valid ? m - r * S : 0;
+
+      if (b != cur_b) {  // FiLM table of this image -> shared memory (rows gamma, beta')
+        const float* f = a.in.film + (size_t)b * 9 * FILM_ROWS * SW;
+        for (int i = ct; i < 9 * 2 * SW; i += TC_COMPUTE) {
+          const int l = i / (2 * SW), row = (i / SW) & 1, n = i % SW;
+          sm.film[l][row][n] = f[(l * FILM_ROWS + (row ? 2 : 0)) * SW + n];
+        }
+        cur_b = b;
+      }
 
       // ---- per-row geometry, recomputed by both column halves ----
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
@@ -225,7 +255,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
           for (int c = 0; c < 3; ++c) pw[c] = __fadd_rn(o[c], __fmul_rn(rd[c], z));
           x0 = __fmul_rn(pw[0], P.pts_scale), x1 = __fmul_rn(pw[1], P.pts_scale),
           x2 = __fmul_rn(pw[2], P.pts_scale);
-          if (ch == 0) {
+          if (hw == 0) {
             float dd;
             if (s + 1 < S) dd = __fsub_rn(z_of(s + 1), z);
             else if (P.flags & E3_RENDER_NO_FORCE_STOP) dd = (S > 1) ? __fsub_rn(z_of(1), z_of(0)) : 0.f;
@@ -258,13 +288,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         }
       }
 
-      // publish the layer's A operand: generic-proxy stores -> visible to the async proxy (UMMA)
-      auto publish_a = [&]() {
-        fence_proxy_async();
-        tc::fence_before_thread_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.a_ready);
-      };
+      compute_sync();  // FiLM table visible; the previous tile's readers of shared arrays are done
 
       // rendering.return_feats: hidden states after 0-based layers 0,2,4,6 (volume_renderer.py:179-180)
       auto store_tap = [&](int tap, int n0, const float* v) {
@@ -273,45 +297,36 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         dst[0] = make_float4(v[0], v[1], v[2], v[3]);
         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       };
+      const bool taps = (MODE == 0) && a.out.feats_taps && valid;
 
-      // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta') ----
-      {
-        const float* gam = film;
-        const float* betp = film + 2 * SW;
+      // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta'), 4 blocks ----
 #pragma unroll 1
-        for (int g8 = 0; g8 < 16; ++g8) {
-          const int n0 = cbase + g8 * 8;
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int n0 = j * 64 + hw * 32 + g8 * 8;
           float v[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 2; ++j4) {
-            const int n = n0 + j4 * 4;
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + n));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + SW + n));
-            const float4 w2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + 2 * SW + n));
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(betp + n));
-            const float acc[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
-                                  fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
-            v[j4 * 4 + 0] = sin_accurate(fmaf(g.x, acc[0], be.x));
-            v[j4 * 4 + 1] = sin_accurate(fmaf(g.y, acc[1], be.y));
-            v[j4 * 4 + 2] = sin_accurate(fmaf(g.z, acc[2], be.z));
-            v[j4 * 4 + 3] = sin_accurate(fmaf(g.w, acc[3], be.w));
+          for (int i = 0; i < 8; ++i) {
+            const int n = n0 + i;
+            const float acc = fmaf(sm.w0[2][n], x2, fmaf(sm.w0[1][n], x1, sm.w0[0][n] * x0));
+            v[i] = sin_fast_accurate(fmaf(sm.film[0][0][n], acc, sm.film[0][1][n]));
           }
           store_a8(sm, m, n0, v);
-          if (MODE == 0 && a.out.feats_taps && valid) store_tap(0, n0, v);
+          if (taps) store_tap(0, n0, v);
         }
-        publish_a();
+        publish(j);
       }
 
-      // ---- hidden layers 1..7: TMEM -> FiLM + sin -> next A operand ----
+      // ---- hidden layers 1..7: TMEM -> FiLM + sin -> next A operand, 64 channels at a time ----
       float sdf_acc = 0.f;
       for (int l = 1; l < 8; ++l) {
         mbar_wait(&sm.d_ready, pd);
         pd ^= 1;
         tc::fence_after_thread_sync();
-        const float* gam = film + (size_t)l * FILM_ROWS * SW;
-        const float* betp = gam + 2 * SW;
+        const uint32_t dsrc = trow + (uint32_t)((l - 1) & 1) * 256;  // GEMM index l-1 -> TMEM half
         const bool last = (l == 7);
+        const bool feed = !last || a.with_view;
         const float* la = nullptr;
         const float* lb = nullptr;
         if (MODE == 0 && last && a.in.local_alpha && valid) {
@@ -319,52 +334,39 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
           lb = a.in.local_beta + (samp0 + m) * SW;
         }
 #pragma unroll 1
-        for (int chunk = 0; chunk < 4; ++chunk) {
+        for (int j = 0; j < 4; ++j) {
           float acc[32];
-          tc::tmem_ld_32x32(trow + chunk * 32, acc);
+          tc::tmem_ld_32x32(dsrc + j * 64, acc);
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
-            const int n0 = cbase + chunk * 32 + g8 * 8;
+            const int n0 = j * 64 + hw * 32 + g8 * 8;
             float v[8];
 #pragma unroll
-            for (int j4 = 0; j4 < 2; ++j4) {
-              const int n = n0 + j4 * 4;
-              const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n));
-              const float4 be = __ldg(reinterpret_cast<const float4*>(betp + n));
-              v[j4 * 4 + 0] = sin_accurate(fmaf(g.x, acc[g8 * 8 + j4 * 4 + 0], be.x));
-              v[j4 * 4 + 1] = sin_accurate(fmaf(g.y, acc[g8 * 8 + j4 * 4 + 1], be.y));
-              v[j4 * 4 + 2] = sin_accurate(fmaf(g.z, acc[g8 * 8 + j4 * 4 + 2], be.z));
-              v[j4 * 4 + 3] = sin_accurate(fmaf(g.w, acc[g8 * 8 + j4 * 4 + 3], be.w));
-            }
+            for (int i = 0; i < 8; ++i)
+              v[i] = sin_fast_accurate(fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]));
             if (last) {
               // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
 #pragma unroll
-              for (int j4 = 0; j4 < 2; ++j4) {
-                const float4 ws = __ldg(reinterpret_cast<const float4*>(pk + OFF_WSIG + n0 + j4 * 4));
-                sdf_acc = fmaf(ws.x, v[j4 * 4 + 0], sdf_acc);
-                sdf_acc = fmaf(ws.y, v[j4 * 4 + 1], sdf_acc);
-                sdf_acc = fmaf(ws.z, v[j4 * 4 + 2], sdf_acc);
-                sdf_acc = fmaf(ws.w, v[j4 * 4 + 3], sdf_acc);
-              }
+              for (int i = 0; i < 8; ++i) sdf_acc = fmaf(sm.wsig[n0 + i], v[i], sdf_acc);
               if (la) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  v[j] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + j], 1.f), v[j]), lb[n0 + j]);
+                for (int i = 0; i < 8; ++i)
+                  v[i] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + i], 1.f), v[i]), lb[n0 + i]);
               }
             }
-            if (MODE == 0 && a.out.feats_taps && (l & 1) == 0 && valid) store_tap(l >> 1, n0, v);
-            if (!last || a.with_view) store_a8(sm, m, n0, v);
+            if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
+            if (feed) store_a8(sm, m, n0, v);
           }
+          if (feed) publish(j);
         }
-        if (!last || a.with_view) publish_a();
-        else tc::fence_before_thread_sync();
+        if (!feed) tc::fence_before_thread_sync();
       }
-      sm.sdf_part[ch][m] = sdf_acc;
+      sm.sdf_part[hw][m] = sdf_acc;
       compute_sync();
 
       // ---- sdf -> sigma -> alpha -> transmittance scan (overlaps the view-layer MMAs) ----
       if (MODE == 0) {
-        if (ch == 0 && valid) {
+        if (hw == 0 && valid) {
           const float sd = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
           float al;
           if (P.flags & E3_RENDER_NO_SDF) {
@@ -411,12 +413,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
           }
         }
         compute_sync();
-        if (ch == 0 && valid) {
+        if (hw == 0 && valid) {
           if (a.out.hit_prob) a.out.hit_prob[samp0 + m] = sm.wgt[m];
           if (a.out.visibility) a.out.visibility[samp0 + m] = sm.vis[m];
         }
       } else {
-        if (ch == 0 && valid) a.p_sdf[samp0 + m] = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
+        if (hw == 0 && valid) a.p_sdf[samp0 + m] = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
       }
 
       if (a.with_view) {
@@ -424,70 +426,66 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         mbar_wait(&sm.d_ready, pd);
         pd ^= 1;
         tc::fence_after_thread_sync();
-        const float* gam = film + (size_t)8 * FILM_ROWS * SW;
-        const float* betp = gam + 2 * SW;
+        const uint32_t dsrc = trow + 256u;  // GEMM index 7 -> TMEM half 1
         const float wrow = (MODE == 0 && valid) ? sm.wgt[m] : 0.f;
         float* fbuf = reinterpret_cast<float*>(sm.a_hi);  // [256][128] fp32 over a_hi + a_lo
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
-        for (int chunk = 0; chunk < 4; ++chunk) {
+        for (int j = 0; j < 4; ++j) {
           float acc[32];
-          tc::tmem_ld_32x32(trow + chunk * 32, acc);
+          tc::tmem_ld_32x32(dsrc + j * 64, acc);
+          const int nb = j * 64 + hw * 32;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const int n = cbase + chunk * 32 + j4 * 4;
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(betp + n));
+            const int n = nb + j4 * 4;
             const float4 d0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + n));
             const float4 d1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + SW + n));
             const float4 d2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + 2 * SW + n));
             const float4 r0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + n));
             const float4 r1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + SW + n));
             const float4 r2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + 2 * SW + n));
-            const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
             const float e0[4] = {d0.x, d0.y, d0.z, d0.w}, e1[4] = {d1.x, d1.y, d1.z, d1.w},
                         e2[4] = {d2.x, d2.y, d2.z, d2.w};
             const float q0[4] = {r0.x, r0.y, r0.z, r0.w}, q1[4] = {r1.x, r1.y, r1.z, r1.w},
                         q2[4] = {r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float pre = acc[j4 * 4 + j];
-              pre = fmaf(e0[j], v0, pre);
-              pre = fmaf(e1[j], v1, pre);
-              pre = fmaf(e2[j], v2, pre);
-              const float f = sin_accurate(fmaf(gg[j], pre, bb[j]));
-              c0 = fmaf(q0[j], f, c0);
-              c1 = fmaf(q1[j], f, c1);
-              c2 = fmaf(q2[j], f, c2);
-              acc[j4 * 4 + j] = f;
+            for (int i = 0; i < 4; ++i) {
+              float pre = acc[j4 * 4 + i];
+              pre = fmaf(e0[i], v0, pre);
+              pre = fmaf(e1[i], v1, pre);
+              pre = fmaf(e2[i], v2, pre);
+              const float f = sin_fast_accurate(fmaf(sm.film[8][0][n + i], pre, sm.film[8][1][n + i]));
+              c0 = fmaf(q0[i], f, c0);
+              c1 = fmaf(q1[i], f, c1);
+              c2 = fmaf(q2[i], f, c2);
+              acc[j4 * 4 + i] = f;
             }
           }
           if (MODE == 1) {
             if (a.p_feat && valid) {
-              float4* dst = reinterpret_cast<float4*>(a.p_feat + (samp0 + m) * SW + cbase + chunk * 32);
+              float4* dst = reinterpret_cast<float4*>(a.p_feat + (samp0 + m) * SW + nb);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+              for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
             }
-          }
-          // stage w*f for the per-ray sum (all view-layer MMAs have completed — d_ready — so the
-          // A-operand region is free; each thread owns its (n, m) slots, no cross-thread hazard)
-          if (MODE == 0) {
+          } else {
+            // stage w*f for the per-ray sum (all view-layer MMAs have completed — d_ready — so the
+            // A-operand region is free; each thread owns its (n, m) slots, no cross-thread hazard)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = cbase + chunk * 32 + j;
-              fbuf[n * TCM + (m ^ (n & 31))] = wrow * acc[j];
+            for (int i = 0; i < 32; ++i) {
+              const int n = nb + i;
+              fbuf[n * TCM + (m ^ (n & 31))] = wrow * acc[i];
             }
           }
         }
-        sm.rgb_part[ch][0][m] = c0;
-        sm.rgb_part[ch][1][m] = c1;
-        sm.rgb_part[ch][2][m] = c2;
+        sm.rgb_part[hw][0][m] = c0;
+        sm.rgb_part[hw][1][m] = c1;
+        sm.rgb_part[hw][2][m] = c2;
         tc::fence_before_thread_sync();
         compute_sync();
 
         if (MODE == 0) {
-          if (a.out.raw_rgb && ch == 0 && valid) {
+          if (a.out.raw_rgb && hw == 0 && valid) {
             float* o = a.out.raw_rgb + (samp0 + m) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -514,7 +512,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
               o[rr] = accum;
             }
           }
-        } else if (a.p_rgb && ch == 0 && valid) {
+        } else if (a.p_rgb && hw == 0 && valid) {
           float* o = a.p_rgb + (samp0 + m) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c)
@@ -527,7 +525,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
 
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream) {

@@ -364,3 +364,19 @@ def test_renderer_backends_agree_at_full_size_and_too_many_samples_is_refused():
     G2, _ = _build(64, 8, 1, "default", n_samples=129, full_pipeline=False)
     with pytest.raises(RuntimeError, match="n_samples"):
         G2.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
+
+
+def test_inversion_record_packing_and_metrics():
+    from e3dge_b200 import parallel as par
+    g = torch.Generator().manual_seed(9)
+    B, n_lat = 3, 6
+    w, wd = torch.randn(B, 9, 256, generator=g), torch.randn(B, n_lat, 512, generator=g)
+    img, tgt = torch.randn(B, 3, 64, 64, generator=g), torch.randn(B, 3, 64, 64, generator=g)
+    rec = par.pack_records(w.cuda(), wd.cuda(), img.cuda(), tgt.cuda()).cpu()
+    assert rec.shape == (B, par.record_length(n_lat))
+    w2, wd2, met = par.unpack_records(rec, n_lat)
+    assert torch.equal(w2, w) and torch.equal(wd2, wd)          # latents: bit-exact copies
+    torch.testing.assert_close(met[:, 0], ((img - tgt) ** 2).flatten(1).mean(1), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(met[:, 1], (img - tgt).abs().flatten(1).mean(1), rtol=1e-5, atol=1e-7)
+    rec0 = par.pack_records(w.cuda(), wd.cuda()).cpu()           # no image: metrics are zero
+    assert torch.equal(rec0[:, -2:], torch.zeros(B, 2))
