@@ -7,13 +7,13 @@
 // (hi*hi, hi*lo, lo*hi) accumulate in fp32 in TMEM, which keeps the decoder within ~1e-5 of
 // the fp32 reference where plain bf16 operands would sit at ~1e-2 (north_star bar: 1e-3).
 //
-// Structure (one CTA per 128-pixel x 128-channel output tile, 6 warps):
+// Structure (persistent CTAs, one per SM, each walking 128-pixel x 128-channel output tiles; 6 warps):
 //   warp 0      TMA producer: 4-D tiled tensor maps over the NHWC bf16 activations
 //               (box = 64 ch x bw x bh x bb pixels, 128B swizzle, out-of-bounds = zero fill, which
 //               *is* the conv's zero padding) and 2-D maps over the K-major weights; 3-stage
 //               full/empty mbarrier ring, 64 KB per stage (A_hi, A_lo, B_hi, B_lo);
-//   warp 1      TMEM allocation + single-thread MMA issue (12 UMMAs 128x128x16 per stage),
-//               tcgen05.commit releases the stage / signals the epilogue;
+//   warp 1      TMEM allocation (2 x 128 columns, ping-pong) + single-thread MMA issue (12 UMMAs
+//               128x128x16 per stage), tcgen05.commit releases the stage / signals the epilogue;
 //   warps 2..5  epilogue: tcgen05.ld (each warp its 32-lane quarter), demodulation + noise +
 //               bias + leaky-ReLU*sqrt(2) (StyledConv, stylesdf_model.py:494-507), fp32 NHWC store.
 #include "tcgen05.cuh"
@@ -115,6 +115,11 @@ struct TcTile {
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
 };
 
+// Persistent: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so neighbouring
+// CTAs share the activation tile in L2).  Two 128-column TMEM accumulators ping-pong: the MMAs of
+// tile i+1 run while the epilogue warps drain tile i.
+constexpr int TC_ACC_BUFS = 2;
+
 template <int TAPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -124,14 +129,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* empty = full + TC_STAGES;
-  uint64_t* accum_bar = empty + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty + TC_STAGES;
+  uint64_t* acc_empty = acc_full + TC_ACC_BUFS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x;
-  const int tx = mt % t.tiles_x, ty = (mt / t.tiles_x) % t.tiles_y, tb = mt / (t.tiles_x * t.tiles_y);
-  const int x0 = tx * t.bw, y0 = ty * t.bh, b0 = tb * t.bb;
-  const int n0 = blockIdx.y * TC_BN;
+  const int n_tiles_n = a.N / TC_BN;
+  const int n_tiles = t.tiles_x * t.tiles_y * t.tiles_b * n_tiles_n;
   const int kpt = a.Cin / TC_BK, nkb = TAPS * kpt;
 
   if (warp == 0 && lane == 0) {
@@ -144,99 +148,130 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_bar, 1);
+#pragma unroll
+    for (int s = 0; s < TC_ACC_BUFS; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, TC_BN);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TC_ACC_BUFS * TC_BN);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
+    const int nt = tile % n_tiles_n, mt = tile / n_tiles_n;
+    const int tx = mt % t.tiles_x, ty = (mt / t.tiles_x) % t.tiles_y, tb = mt / (t.tiles_x * t.tiles_y);
+    x0 = tx * t.bw, y0 = ty * t.bh, b0 = tb * t.bb, n0 = nt * TC_BN;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int tap = kb / kpt, kc = kb - tap * kpt;
-        const int dx = (TAPS == 9) ? tap % 3 - 1 : 0, dy = (TAPS == 9) ? tap / 3 - 1 : 0;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
-        uint8_t* st = smem + stage * TC_STAGE_BYTES;
-        tc::tma_load_4d(st, &tmA_hi, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
-        tc::tma_load_4d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
-        tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[stage], tap * a.Cin + kc * TC_BK, n0);
-        tc::tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[stage], tap * a.Cin + kc * TC_BK, n0);
-        if (++stage == TC_STAGES) {
-          stage = 0;
-          phase ^= 1;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int x0, y0, b0, n0;
+        tile_coords(tile, x0, y0, b0, n0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / kpt, kc = kb - tap * kpt;
+          const int dx = (TAPS == 9) ? tap % 3 - 1 : 0, dy = (TAPS == 9) ? tap / 3 - 1 : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+          uint8_t* st = smem + stage * TC_STAGE_BYTES;
+          tc::tma_load_4d(st, &tmA_hi, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
+          tc::tma_load_4d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
+          tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[stage], tap * a.Cin + kc * TC_BK, n0);
+          tc::tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[stage], tap * a.Cin + kc * TC_BK, n0);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, TC_BN);
-      uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
         tc::fence_after_thread_sync();
-        const uint32_t sb = smem_u32(smem + stage * TC_STAGE_BYTES);
-        const uint64_t dA_hi = tc::make_smem_desc_sw128(sb);
-        const uint64_t dA_lo = tc::make_smem_desc_sw128(sb + TC_TILE_BYTES);
-        const uint64_t dB_hi = tc::make_smem_desc_sw128(sb + 2 * TC_TILE_BYTES);
-        const uint64_t dB_lo = tc::make_smem_desc_sw128(sb + 3 * TC_TILE_BYTES);
+        const uint32_t dcol = tmem_base + buf * TC_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc::fence_after_thread_sync();
+          const uint32_t sb = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint64_t dA_hi = tc::make_smem_desc_sw128(sb);
+          const uint64_t dA_lo = tc::make_smem_desc_sw128(sb + TC_TILE_BYTES);
+          const uint64_t dB_hi = tc::make_smem_desc_sw128(sb + 2 * TC_TILE_BYTES);
+          const uint64_t dB_lo = tc::make_smem_desc_sw128(sb + 3 * TC_TILE_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < TC_BK / 16; ++ks) {
-          const uint64_t ah = tc::advance_desc_k(dA_hi, ks), al = tc::advance_desc_k(dA_lo, ks);
-          const uint64_t bh = tc::advance_desc_k(dB_hi, ks), bl = tc::advance_desc_k(dB_lo, ks);
-          tc::mma_bf16_ss(tmem_base, ah, bh, idesc, (kb | ks) != 0);
-          tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
-          tc::mma_bf16_ss(tmem_base, al, bh, idesc, true);
+          for (int ks = 0; ks < TC_BK / 16; ++ks) {
+            const uint64_t ah = tc::advance_desc_k(dA_hi, ks), al = tc::advance_desc_k(dA_lo, ks);
+            const uint64_t bh = tc::advance_desc_k(dB_hi, ks), bl = tc::advance_desc_k(dB_lo, ks);
+            tc::mma_bf16_ss(dcol, ah, bh, idesc, (kb | ks) != 0);
+            tc::mma_bf16_ss(dcol, ah, bl, idesc, true);
+            tc::mma_bf16_ss(dcol, al, bh, idesc, true);
+          }
+          tc::mma_commit(&empty[stage]);  // the stage is free once these MMAs have read it
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        tc::mma_commit(&empty[stage]);  // the stage is free once these MMAs have read it
-        if (++stage == TC_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        tc::mma_commit(&acc_full[buf]);
       }
-      tc::mma_commit(accum_bar);
     }
   } else {
     // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to warp q = warp % 4 =====
-    mbar_wait(accum_bar, 0);
-    tc::fence_after_thread_sync();
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int ix = m % t.bw, iy = (m / t.bw) % t.bh, ib = m / (t.bw * t.bh);
-    const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
-    const bool valid = b < a.B;
-    const int p = y * a.W + x;
     const float nw = (a.mode == 1) ? a.noise_w[0] : 0.f;
-    const float nz = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
-    float* orow = a.out + (((size_t)(valid ? b : 0) * a.H + y) * a.W + x) * a.N + n0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      int x0, y0, b0, n0;
+      tile_coords(tile, x0, y0, b0, n0);
+      const uint32_t buf = it & 1, use = it >> 1;
+      const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
+      const bool valid = b < a.B;
+      const int p = y * a.W + x;
+      const float nz = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
+      float* orow = a.out + (((size_t)(valid ? b : 0) * a.H + y) * a.W + x) * a.N + n0;
+      mbar_wait(&acc_full[buf], use & 1);
+      tc::fence_after_thread_sync();
 #pragma unroll 1
-    for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
-      float v[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + chunk * 32, v);
-      if (!valid) continue;
-      const int nb = n0 + chunk * 32;
-      if (a.mode == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float tt = fmaf(v[j], a.d[(size_t)b * a.N + nb + j], nz) + a.act_bias[nb + j];
-          v[j] = (tt > 0.f ? tt : 0.2f * tt) * 1.41421356237309515f;
+      for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+        float v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
+        if (chunk == TC_BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-      } else if (a.mode == 2) {
+        if (!valid) continue;
+        const int nb = n0 + chunk * 32;
+        if (a.mode == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= a.d[(size_t)b * a.N + nb + j];
+          for (int j = 0; j < 32; ++j) {
+            const float tt = fmaf(v[j], a.d[(size_t)b * a.N + nb + j], nz) + a.act_bias[nb + j];
+            v[j] = (tt > 0.f ? tt : 0.2f * tt) * 1.41421356237309515f;
+          }
+        } else if (a.mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= a.d[(size_t)b * a.N + nb + j];
+        }
+        float4* dst = reinterpret_cast<float4*>(orow + chunk * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-      float4* dst = reinterpret_cast<float4*>(orow + chunk * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, TC_BN);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TC_ACC_BUFS * TC_BN);
 }
 
 bool tc_conv_supported(int B, int H, int W, int Cin, int N) {
@@ -307,7 +342,8 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set[which] = true;
   }
-  dim3 grid(t.tiles_x * t.tiles_y * t.tiles_b, a.N / TC_BN);
+  const int n_tiles = t.tiles_x * t.tiles_y * t.tiles_b * (a.N / TC_BN);
+  dim3 grid(n_tiles < sm_count() ? n_tiles : sm_count());
   if (taps == 9)
     tc_conv_kernel<9><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a, t);
   else
