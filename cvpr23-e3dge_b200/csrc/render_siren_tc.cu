@@ -15,7 +15,7 @@
 //     parity bar is 1e-3);
 //   * weights: 2 MB of pre-split, pre-swizzled bf16 tiles streamed from L2 by cp.async.bulk
 //     (TMA) through a 4 x 16 KB full/empty mbarrier ring, one 128(n) x 64(k) tile per stage;
-//   * 8 epilogue warps: tcgen05.ld -> FiLM (bias folded into beta', table in shared memory) ->
+//   * 16 epilogue warps: tcgen05.ld -> FiLM (bias folded into beta', table in shared memory) ->
 //     accurate sin -> hi/lo split -> swizzled st.shared of the next layer's A operand; layer 0
 //     (K = 3), the sdf / rgb heads, the view-direction rank-3 update, the transmittance scan and
 //     the weighted feature sum stay on the CUDA cores.
@@ -29,8 +29,8 @@
 // because layer l's MMAs have all completed (d_ready) before its epilogue starts.
 //
 // Warp roles: warp 0 = TMA weight producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 =
-// compute (TMEM lane quarter = warp % 4; the two warps of a quarter take 32 columns each of a
-// 64-channel block).  The sdf->alpha->scan work of a tile overlaps with the view-layer MMAs.
+// compute (TMEM lane quarter = warp % 4; the four warps of a quarter take 16 columns each of a
+// 64-channel block — 4 warps per scheduler hide the sin / LDS / tcgen05.ld latencies).  The sdf->alpha->scan work of a tile overlaps with the view-layer MMAs.
 #include <cuda_bf16.h>
 
 #include "render_siren.cuh"
@@ -40,7 +40,7 @@ namespace e3 {
 
 constexpr int TCM = 128;                 // rows per tile
 constexpr int TC_RING = 4;               // weight stages
-constexpr int TC_COMPUTE_WARPS = 8;
+constexpr int TC_COMPUTE_WARPS = 16;
 constexpr int TC_COMPUTE = TC_COMPUTE_WARPS * 32;
 constexpr int TC_NTHREADS = 64 + TC_COMPUTE;  // producer warp + MMA warp + compute warps
 constexpr int A_KBLOCK_BYTES = TCM * 128;      // 128 rows x 64 bf16
@@ -51,11 +51,10 @@ struct SmemTC {
   uint8_t a_lo[A_BYTES];
   uint8_t ring[TC_RING * TC_TILE_BYTES];
   float film[9][2][SW];   // gamma, beta' = gamma*bias + beta of the current image
-  float w0[3][SW];        // layer-0 weights, natural channel order
   float wsig[SW];
   float z[TCM], dist[TCM], alpha[TCM], wgt[TCM], vis[TCM];
-  float sdf_part[2][TCM];
-  float rgb_part[2][3][TCM];
+  float sdf_part[4][TCM];   // partial head sums of the 4 column quarters
+  float rgb_part[4][3][TCM];
   float ray_o[3][TCM], ray_d[3][TCM];
   uint64_t full[TC_RING], empty[TC_RING];
   uint64_t a_ready[4], d_ready;
@@ -107,7 +106,6 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
     mbar_init(&sm.d_ready, 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < 3 * SW; i += TC_NTHREADS) sm.w0[0][i] = a.packed[OFF_W0N + i];
   for (int i = tid; i < SW; i += TC_NTHREADS) sm.wsig[i] = a.packed[OFF_WSIG + i];
   if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_before_thread_sync();
@@ -183,11 +181,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
   } else {
     // ===== compute warps =====
     const e3_render_params& P = a.p;
-    const int ct = tid - 64;              // 0..255
+    const int ct = tid - 64;              // 0..511
     const int q = warp & 3;               // TMEM lane quarter this warp may read
-    const int hw = (warp - 2) >> 2;       // which 32-column half of each 64-channel block
+    const int hw = (warp - 2) >> 2;       // which 16-column quarter of each 64-channel block (0..3)
     const int m = q * 32 + lane;          // tile row = TMEM lane
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + hw * 32;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + hw * 16;
     const int S = (MODE == 0) ? P.n_samples : 1;
     const int HW = (MODE == 0) ? P.height * P.width : a.n_points;
     const float* pk = a.packed;
@@ -303,14 +301,20 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int n0 = j * 64 + hw * 32 + g8 * 8;
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int n0 = j * 64 + hw * 16 + g8 * 8;
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = n0 + i;
-            const float acc = fmaf(sm.w0[2][n], x2, fmaf(sm.w0[1][n], x1, sm.w0[0][n] * x0));
-            v[i] = sin_fast_accurate(fmaf(sm.film[0][0][n], acc, sm.film[0][1][n]));
+          for (int i4 = 0; i4 < 2; ++i4) {
+            const int n = n0 + i4 * 4;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + n));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + SW + n));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + 2 * SW + n));
+            const float a4[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
+                                 fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              v[i4 * 4 + i] = sin_fast_accurate(fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]));
           }
           store_a8(sm, m, n0, v);
           if (taps) store_tap(0, n0, v);
@@ -335,11 +339,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-          float acc[32];
-          tc::tmem_ld_32x32(dsrc + j * 64, acc);
+          float acc[16];
+          tc::tmem_ld_32x16(dsrc + j * 64, acc);
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int n0 = j * 64 + hw * 32 + g8 * 8;
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const int n0 = j * 64 + hw * 16 + g8 * 8;
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -367,7 +371,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       // ---- sdf -> sigma -> alpha -> transmittance scan (overlaps the view-layer MMAs) ----
       if (MODE == 0) {
         if (hw == 0 && valid) {
-          const float sd = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
+          const float sd = (sm.sdf_part[0][m] + sm.sdf_part[1][m]) + (sm.sdf_part[2][m] + sm.sdf_part[3][m]) + pk[OFF_HEADB];
           float al;
           if (P.flags & E3_RENDER_NO_SDF) {
             const float sp = (sd > 20.f) ? sd : log1pf(expf(sd));
@@ -418,7 +422,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
           if (a.out.visibility) a.out.visibility[samp0 + m] = sm.vis[m];
         }
       } else {
-        if (hw == 0 && valid) a.p_sdf[samp0 + m] = sm.sdf_part[0][m] + sm.sdf_part[1][m] + pk[OFF_HEADB];
+        if (hw == 0 && valid)
+          a.p_sdf[samp0 + m] = (sm.sdf_part[0][m] + sm.sdf_part[1][m]) + (sm.sdf_part[2][m] + sm.sdf_part[3][m]) + pk[OFF_HEADB];
       }
 
       if (a.with_view) {
@@ -432,11 +437,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-          float acc[32];
-          tc::tmem_ld_32x32(dsrc + j * 64, acc);
-          const int nb = j * 64 + hw * 32;
+          float acc[16];
+          tc::tmem_ld_32x16(dsrc + j * 64, acc);
+          const int nb = j * 64 + hw * 16;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
+          for (int j4 = 0; j4 < 4; ++j4) {
             const int n = nb + j4 * 4;
             const float4 d0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + n));
             const float4 d1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + SW + n));
@@ -465,14 +470,14 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
             if (a.p_feat && valid) {
               float4* dst = reinterpret_cast<float4*>(a.p_feat + (samp0 + m) * SW + nb);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < 4; ++i)
                 dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
             }
           } else {
             // stage w*f for the per-ray sum (all view-layer MMAs have completed — d_ready — so the
             // A-operand region is free; each thread owns its (n, m) slots, no cross-thread hazard)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               const int n = nb + i;
               fbuf[n * TCM + (m ^ (n & 31))] = wrow * acc[i];
             }
@@ -489,20 +494,22 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
             float* o = a.out.raw_rgb + (samp0 + m) * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-              o[c] = sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m] + pk[OFF_HEADB + 1 + c];
+              o[c] = (sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m]) + (sm.rgb_part[2][c][m] + sm.rgb_part[3][c][m]) +
+                     pk[OFF_HEADB + 1 + c];
           }
           if (a.out.thumb_rgb && ct < 3 * n_units) {
             const int c = ct / n_units, rr = ct - c * n_units;
             float accum = 0.f;
             for (int si = 0; si < S; ++si) {
               const int mm = rr * S + si;
-              const float raw = sm.rgb_part[0][c][mm] + sm.rgb_part[1][c][mm] + pk[OFF_HEADB + 1 + c];
+              const float raw = (sm.rgb_part[0][c][mm] + sm.rgb_part[1][c][mm]) +
+                                (sm.rgb_part[2][c][mm] + sm.rgb_part[3][c][mm]) + pk[OFF_HEADB + 1 + c];
               accum = fmaf(sm.wgt[mm], sigmoid_acc(raw), accum);
             }
             a.out.thumb_rgb[((size_t)b * 3 + c) * HW + unit0 + rr] = -1.f + 2.f * accum;
           }
-          if (a.out.features) {
-            const int n = ct;  // one output channel per compute thread
+          if (a.out.features && ct < SW) {
+            const int n = ct;  // one output channel per thread (first 256 compute threads)
             const float* row = fbuf + n * TCM;
             const int sw = n & 31;
             float* o = a.out.features + ((size_t)b * SW + n) * HW + unit0;
@@ -516,7 +523,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
           float* o = a.p_rgb + (samp0 + m) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            o[c] = sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m] + pk[OFF_HEADB + 1 + c];
+            o[c] = (sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m]) + (sm.rgb_part[2][c][m] + sm.rgb_part[3][c][m]) +
+                   pk[OFF_HEADB + 1 + c];
         }
       }
       compute_sync();  // shared memory is reused by the next tile

@@ -380,3 +380,82 @@ def test_inversion_record_packing_and_metrics():
     torch.testing.assert_close(met[:, 1], (img - tgt).abs().flatten(1).mean(1), rtol=1e-5, atol=1e-7)
     rec0 = par.pack_records(w.cuda(), wd.cuda()).cpu()           # no image: metrics are zero
     assert torch.equal(rec0[:, -2:], torch.zeros(B, 2))
+
+
+def test_sample_mode_geometry_queries_and_init_pass():
+    """sample_mode (synthetic-data sampler, data_util.py:74), geometry_sample re-queries and the
+    sphere-init pass: random points are drawn on the device, so the sdf values the renderer returns
+    are checked against the oracle evaluated at those same points."""
+    size, res, seed = 64, 8, 515
+    G, sd = _build(size, res, seed, "sharp", full_pipeline=False, sample_near_surface=True,
+                   sample_uniform_grid=True, uniform_grid_sampling_num=300)
+    inp = P.make_inputs(seed, 2, 1, res)
+    d = _cuda(inp)
+    with torch.no_grad():
+        out = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"], sample_mode=True)
+    B = 2
+    n_near = res * res
+    assert out["uniform_pts"].shape == (B, n_near + 300, 1, 1, 3)
+    assert out["uniform_points_sdf"].shape == (B, n_near + 300, 1, 1, 1)
+    assert out["uniform_points_valid_mask"].shape == (B, n_near + 300, 1, 1, 1)
+    assert out["xyz"].shape == (B, res, res, 3) and out["mask"].shape == (B, res, res, 1, 1)
+    pts = out["uniform_pts"].reshape(B, -1, 3).cpu()
+    with torch.no_grad():
+        # near-surface points were queried WITH the ray view directions, grid points with zeros; the sdf
+        # head does not depend on the view direction, so one oracle query covers both
+        ref = O.sdf_query(sd, pts, inp["w"])
+    assert rel_linf(out["uniform_points_sdf"].reshape(B, -1, 1).cpu(), ref) < TOL
+    assert G.renderer.sample_mode is False  # flag flips back (volume_renderer.py:1970-1971)
+    # geometry_sample: sdf re-queried at caller points
+    q = torch.rand(B, 50, 1, 1, 3, device="cuda") * 0.2 - 0.1
+    with torch.no_grad():
+        out2 = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"],
+                          geometry_sample={"uniform_pts": q, "xyz": None})
+        ref2 = O.sdf_query(sd, q.reshape(B, -1, 3).cpu(), inp["w"])
+    assert out2["uniform_pts_rec"].shape == (B, 50, 1, 1, 1)
+    assert rel_linf(out2["uniform_pts_rec"].reshape(B, -1, 1).cpu(), ref2) < TOL
+    # sphere-init pass: target = |p| - (far - near)/4
+    with torch.no_grad():
+        sdf, target = G.renderer.mlp_init_pass(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
+    assert sdf.shape == target.shape == (B, res, res, 24)
+    assert torch.isfinite(sdf).all() and (target.abs() < 2).all()
+
+
+def test_tuple_generator_truncation_mean_latent_and_perturbed_sampling():
+    from e3dge_b200 import model_options, rendering_options
+    from e3dge_b200.stylesdf_model import Generator
+    size, res, seed = 64, 16, 616
+    sd = synthetic_state_dict(size, res, seed, "default")
+    G = Generator(model_options(size=size, renderer_spatial_output_dim=res), rendering_options()).eval()
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda()
+    inp = P.make_inputs(seed, 2, decoder_layout(size, res), res, wplus=False)
+    z = torch.from_numpy(np.random.Generator(np.random.PCG64(seed)).standard_normal((2, 256)).astype(np.float32))
+    d = _cuda(inp)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        mean = G.mean_latent(64, "cuda")
+        assert mean[0].shape == (1, 256) and mean[1].shape == (1, 512)
+        rgb, thumb, xyz, sdf, mask = G([z.cuda()], d["cam_poses"], d["focal"], d["near"], d["far"],
+                                       truncation=0.6, truncation_latent=mean, randomize_noise=False,
+                                       return_xyz=True, return_sdf=True)
+        w = O.mapping_network(z, sd)
+        w_t = mean[0].cpu() + 0.6 * (w - mean[0].cpu())
+        ref = O.renderer_forward(sd, inp["cam_poses"], inp["focal"], inp["near"], inp["far"], w_t, res=res)
+        wd = O.decoder_mapping(w_t, sd)
+        wd_t = mean[1].cpu() + 0.6 * (wd - mean[1].cpu())
+        n_lat = decoder_layout(size, res)
+        ref_img = O.decoder_forward(sd, ref["features"], wd_t.unsqueeze(1).repeat(1, n_lat, 1))
+    assert rel_linf(thumb.cpu(), ref["gen_thumb_imgs"]) < TOL and rel_linf(sdf.cpu(), ref["sdf"]) < TOL
+    assert rel_linf(rgb.cpu(), ref_img) < TOL
+    assert xyz.shape == (2, 3, res, res) and mask.shape == (2, 1, res, res, 1)
+    # perturb > 0 (training): jittered samples stay inside [near, far) and keep their order
+    from e3dge_b200.volume_renderer import VolumeFeatureRenderer
+    R = VolumeFeatureRenderer(rendering_options(perturb=1.0), out_im_res=res)
+    R.load_state_dict({k[len("renderer."):]: v for k, v in sd.items() if k.startswith("renderer.")})
+    R = R.cuda()
+    with torch.no_grad():
+        o = R(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"])
+    zs = ((o["points"] - o["rays_o"].unsqueeze(3)) / o["rays_d"].unsqueeze(3))[..., 2]
+    assert (zs[..., 1:] > zs[..., :-1]).all() and zs.min() >= 0.88 - 1e-4 and zs.max() < 1.12 + 1e-4
+    assert (o["hit_prob"].sum(3) - 1).abs().max().item() < 1e-5
