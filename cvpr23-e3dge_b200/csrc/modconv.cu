@@ -333,6 +333,9 @@ struct ToRgbArgs {
   int B, H, W, cin;
 };
 
+// One thread per pixel: the pixel's cin fp32 channels are contiguous (NHWC), read as float4 through
+// L1 (each 128-byte line is consumed over 8 consecutive iterations of the same thread); the three
+// modulated weight rows sit in shared memory and are broadcast.  No cross-thread reduction.
 __global__ void __launch_bounds__(256) torgb_kernel(const __grid_constant__ ToRgbArgs a) {
   extern __shared__ float ws[];  // [3][cin] = scale * W[c,i] * s[b,i]
   const int b = blockIdx.y, HW = a.H * a.W;
@@ -340,26 +343,23 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __grid_constant__ ToRg
   for (int i = threadIdx.x; i < 3 * a.cin; i += blockDim.x)
     ws[i] = scale * a.w[i] * a.s[(size_t)b * a.cin + (i % a.cin)];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float kb[4] = {0.25f, 0.75f, 0.75f, 0.25f};  // flipped == itself (symmetric)
-  for (int p = blockIdx.x * 8 + warp; p < HW; p += gridDim.x * 8) {
-    const float* xp = a.x + ((size_t)b * HW + p) * a.cin;
-    float r = 0.f, g = 0.f, bl = 0.f;
-    for (int i = lane * 4; i < a.cin; i += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(xp + i);
-      const float4 w0 = *reinterpret_cast<const float4*>(ws + i);
-      const float4 w1 = *reinterpret_cast<const float4*>(ws + a.cin + i);
-      const float4 w2 = *reinterpret_cast<const float4*>(ws + 2 * a.cin + i);
-      r = fmaf(v.x, w0.x, fmaf(v.y, w0.y, fmaf(v.z, w0.z, fmaf(v.w, w0.w, r))));
-      g = fmaf(v.x, w1.x, fmaf(v.y, w1.y, fmaf(v.z, w1.z, fmaf(v.w, w1.w, g))));
-      bl = fmaf(v.x, w2.x, fmaf(v.y, w2.y, fmaf(v.z, w2.z, fmaf(v.w, w2.w, bl))));
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const float4* xp = reinterpret_cast<const float4*>(a.x + ((size_t)b * HW + p) * a.cin);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int i4 = 0; i4 < a.cin / 4; ++i4) {
+      const float4 v = xp[i4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(ws + c * a.cin + i4 * 4);
+        acc[c] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[c]))));
+      }
     }
-    r = warp_sum(r), g = warp_sum(g), bl = warp_sum(bl);
-    if (lane < 3) {
-      const int c = lane;
-      float v = (c == 0 ? r : (c == 1 ? g : bl)) + a.bias[c];
+    const int Y = p / a.W, X = p - Y * a.W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = acc[c] + a.bias[c];
       if (a.skip) {
-        const int Y = p / a.W, X = p - Y * a.W;
         if (a.upsample_skip) {
           // upfirdn2d(skip, outer(kb,kb), up=2, pad=(2,1)): U[2i]=skip[i]; P[y]=U[y-2]
           const int h2 = a.H >> 1, w2 = a.W >> 1;
@@ -585,7 +585,7 @@ extern "C" int e3_torgb_fwd(const float* x, const float* weight, const float* s,
   if (batch == 0) return E3_OK;
   E3_REQUIRE(x && weight && s && bias && rgb, E3_ERR_BAD_ARG, "e3_torgb_fwd: null argument");
   ToRgbArgs a{x, weight, s, bias, skip, upsample_skip, rgb, batch, h, w, cin};
-  int bx = (h * w + 7) / 8;
+  int bx = (h * w + 255) / 256;
   const int cap = sm_count() * 8;
   if (bx > cap) bx = cap;
   torgb_kernel<<<dim3(bx, batch), 256, 3 * cin * sizeof(float), as_stream(stream)>>>(a);

@@ -45,6 +45,9 @@ constexpr int TC_COMPUTE = TC_COMPUTE_WARPS * 32;
 constexpr int TC_NTHREADS = 64 + TC_COMPUTE;  // producer warp + MMA warp + compute warps
 constexpr int A_KBLOCK_BYTES = TCM * 128;      // 128 rows x 64 bf16
 constexpr int A_BYTES = 4 * A_KBLOCK_BYTES;    // one of hi / lo: 64 KB
+// timing experiments only (profiles/whatif_render.py): results are numerically WRONG with these set
+constexpr uint32_t DBG_SKIP_LO_MMA = 1u << 30;  // issue only the hi*hi products (1/3 of the MMAs)
+constexpr uint32_t DBG_NO_SIN = 1u << 31;       // epilogue without the sin evaluation
 
 struct SmemTC {
   uint8_t a_hi[A_BYTES];  // also the fp32 [256][128] composite buffer together with a_lo
@@ -140,6 +143,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16_f32(128, 128);
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
+      const bool skip_lo = (a.p.flags & DBG_SKIP_LO_MMA) != 0;
       uint32_t stage = 0, phase = 0, pa = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         for (int l = 0; l < gemm_layers; ++l) {  // l-th GEMM of the tile = reference layer l+1
@@ -161,8 +165,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
                 const uint64_t bk = tc::advance_desc_k(dB, ks);
                 if (!is_lo) {
                   tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
-                  tc::mma_bf16_ss(d, tc::advance_desc_k(dAl, ks), bk, idesc, true);
-                } else {
+                  if (!skip_lo) tc::mma_bf16_ss(d, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+                } else if (!skip_lo) {
                   tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, true);
                 }
               }
@@ -191,6 +195,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
     const float* pk = a.packed;
     uint32_t pd = 0;
     int cur_b = -1;
+    const bool no_sin = (P.flags & DBG_NO_SIN) != 0;
 
     // publish k-block j of the next A operand: generic-proxy stores -> async proxy (UMMA)
     auto publish = [&](int j) {
@@ -346,8 +351,10 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
             const int n0 = j * 64 + hw * 16 + g8 * 8;
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              v[i] = sin_fast_accurate(fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]));
+            for (int i = 0; i < 8; ++i) {
+              const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
+              v[i] = no_sin ? arg * 1e-3f : sin_fast_accurate(arg);
+            }
             if (last) {
               // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
 #pragma unroll
