@@ -78,6 +78,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
       : "memory");
 }
 
+// Multicast variant: this CTA fetches `bytes` once and the hardware writes them to the same shared
+// memory offset of every CTA in `cta_mask`, signalling complete_tx on each destination's mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s_multicast(void* smem_dst, const void* gmem_src,
+                                                       uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], "
+      "%2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // sin(x) accurate to <= 1.5 ulp for |x| < 2^15: 3-term Cody-Waite reduction to
 // [-pi/4, pi/4] + minimax polynomials.  FiLM pre-activations reach |x| ~ 1e2, where
 // sin.approx (MUFU) does not hold the 1e-3 end-to-end parity bar.

@@ -32,6 +32,7 @@
 // compute (TMEM lane quarter = warp % 4; the four warps of a quarter take 16 columns each of a
 // 64-channel block — 4 warps per scheduler hide the sin / LDS / tcgen05.ld latencies).  The sdf->alpha->scan work of a tile overlaps with the view-layer MMAs.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "render_siren.cuh"
 #include "tcgen05.cuh"
@@ -91,7 +92,13 @@ __device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float*
   *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-template <int MODE>
+// CL = thread-block cluster size.  The weight stream is identical for every tile, so the CTAs of a
+// cluster share it: each fetches 1/CL of every 16 KB weight tile and TMA-multicasts it into all CL
+// rings (cp.async.bulk ... .multicast::cluster).  A ring stage is recycled when every CTA of the
+// cluster has consumed it (tcgen05.commit multicast onto all CL `empty` barriers, count = CL).  This
+// divides the L2 -> SM traffic of the stream by CL and multiplies the bytes each SM has in flight,
+// which is what bounds the kernel at CL = 1 (profiles/r01e_whatif_render.txt).
+template <int MODE, int CL>
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -102,7 +109,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
 #pragma unroll
     for (int s = 0; s < TC_RING; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], CL);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], TC_COMPUTE_WARPS);
@@ -113,11 +120,15 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
   if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 512);
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any multicast lands
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = sm.tmem_slot;
 
-  const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // every CTA runs the same number of tile slots (the cluster shares one weight stream); slots past
+  // the last tile are dummies that only keep the pipeline in step
+  const int n_my_tiles = (a.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int gemm_layers = a.with_view ? 8 : 7;
+  const uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) {
     // ===== TMA producer: 16 weight tiles per layer, in consumption order =====
@@ -129,8 +140,15 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         for (int c = 0; c < per_tile; ++c) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&sm.full[stage], TC_TILE_BYTES);
-          tma_bulk_g2s(sm.ring + stage * TC_TILE_BYTES, stream + (size_t)c * TC_TILE_BYTES,
-                       TC_TILE_BYTES, &sm.full[stage]);
+          if (CL == 1) {
+            tma_bulk_g2s(sm.ring + stage * TC_TILE_BYTES, stream + (size_t)c * TC_TILE_BYTES,
+                         TC_TILE_BYTES, &sm.full[stage]);
+          } else {
+            constexpr uint32_t slice = TC_TILE_BYTES / CL;
+            const uint32_t off = cluster_ctarank() * slice;
+            tma_bulk_g2s_multicast(sm.ring + stage * TC_TILE_BYTES + off,
+                                   stream + (size_t)c * TC_TILE_BYTES + off, slice, &sm.full[stage], cl_mask);
+          }
           if (++stage == TC_RING) {
             stage = 0;
             phase ^= 1;
@@ -170,7 +188,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
                   tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, true);
                 }
               }
-              tc::mma_commit(&sm.empty[stage]);
+              if (CL == 1) tc::mma_commit(&sm.empty[stage]);
+              else tc::mma_commit_multicast(&sm.empty[stage], cl_mask);
               if (++stage == TC_RING) {
                 stage = 0;
                 phase ^= 1;
@@ -205,11 +224,14 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       if (lane == 0) mbar_arrive(&sm.a_ready[j]);
     };
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int slot = 0; slot < n_my_tiles; ++slot) {
+      const int tile_raw = blockIdx.x + slot * gridDim.x;
+      const bool dummy = tile_raw >= a.n_tiles;  // keeps this CTA in step with its cluster
+      const int tile = dummy ? a.n_tiles - 1 : tile_raw;
       const int b = tile / a.tiles_per_image;
       const int t_in = tile - b * a.tiles_per_image;
       const int unit0 = t_in * a.rays_per_tile;
-      const int n_units = min(a.rays_per_tile, HW - unit0);
+      const int n_units = dummy ? 0 : min(a.rays_per_tile, HW - unit0);
       const int n_valid = n_units * S;
       const size_t samp0 = ((size_t)b * HW + unit0) * S;
       const bool valid = m < n_valid;
@@ -540,25 +562,68 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
 
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into its ring
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream) {
-  static thread_local bool attr_set[2] = {false, false};
+template <int MODE, int CL>
+static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
+  static thread_local bool attr_set = false;
   const int smem_bytes = (int)sizeof(SmemTC) + 1024;
-  const void* fn = (mode == 0) ? (const void*)siren_render_tc_kernel<0> : (const void*)siren_render_tc_kernel<1>;
-  if (!attr_set[mode]) {
+  auto* fn = siren_render_tc_kernel<MODE, CL>;
+  if (!attr_set) {
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set[mode] = true;
+    attr_set = true;
   }
-  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  if (grid <= 0) return E3_OK;
-  if (mode == 0)
-    siren_render_tc_kernel<0><<<grid, TC_NTHREADS, smem_bytes, stream>>>(a);
-  else
-    siren_render_tc_kernel<1><<<grid, TC_NTHREADS, smem_bytes, stream>>>(a);
-  E3_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(TC_NTHREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent kernel: never more CTAs than can be co-resident as whole clusters (GPCs of 16/18/20
+  // SMs cannot all be tiled by clusters of 4)
+  static thread_local int max_clusters = 0;
+  if (!max_clusters) {
+    cfg.gridDim = dim3(((sm_count() + CL - 1) / CL) * CL);
+    int n = 0;
+    E3_CUDA(cudaOccupancyMaxActiveClusters(&n, fn, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  int clusters = (a.n_tiles + CL - 1) / CL;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cfg.gridDim = dim3(clusters * CL);
+  E3_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
   return E3_OK;
+}
+
+// Cluster size of the shared weight stream; E3DGE_RENDER_CLUSTER=1|2|4 overrides (measurement aid).
+static int render_cluster_size() {
+  static int cached = 0;
+  if (!cached) {
+    const char* e = getenv("E3DGE_RENDER_CLUSTER");
+    const int v = e ? atoi(e) : 0;
+    cached = (v == 1 || v == 2 || v == 4) ? v : 2;
+  }
+  return cached;
+}
+
+int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream) {
+  if (a.n_tiles <= 0) return E3_OK;
+  const int cl = render_cluster_size();
+  if (mode == 0) {
+    if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
+    if (cl == 2) return launch_tc_variant<0, 2>(a, stream);
+    return launch_tc_variant<0, 1>(a, stream);
+  }
+  if (cl == 4) return launch_tc_variant<1, 4>(a, stream);
+  if (cl == 2) return launch_tc_variant<1, 2>(a, stream);
+  return launch_tc_variant<1, 1>(a, stream);
 }
 
 }  // namespace e3

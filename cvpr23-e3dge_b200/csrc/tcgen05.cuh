@@ -84,6 +84,15 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// same, arriving on the barrier at this shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---- TMEM -> registers: 32 lanes (this warp's quarter) x 32 consecutive fp32 columns -----------
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

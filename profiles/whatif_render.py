@@ -1,13 +1,14 @@
 #!/usr/bin/env python
-"""What-if timings of the tensor-core render kernel (B=8, 64x64x24): which side bounds the
-k-block-pipelined layer loop?  Uses the kernel's timing-only debug flag bits (results are
-numerically wrong with them set).  Run under gpurun; prints one line per variant."""
-import os, sys, statistics, ctypes
+"""Timings of the tensor-core render kernel (B=8, 64x64x24) under what-if variants:
+  * cluster size of the shared (TMA-multicast) weight stream: E3DGE_RENDER_CLUSTER=1|2|4
+    (one process per value: the choice is cached at first launch);
+  * timing-only debug flag bits (skip the lo MMA passes / skip the sin) — numerically WRONG results.
+Run under gpurun:  for c in 1 2 4; do E3DGE_RENDER_CLUSTER=$c python profiles/whatif_render.py; done"""
+import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "cvpr23-e3dge_b200"), os.path.join(ROOT, "tests")]
 import torch
 import bench
-from e3dge_b200 import _lib
 
 dev = torch.device("cuda", 0)
 G, sd = bench.build_generator(dev)
@@ -15,6 +16,7 @@ inp = {k: v.to(dev) for k, v in bench.make_inputs(0).items()}
 R = G.renderer
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 base = R._flags()
+cl = os.environ.get("E3DGE_RENDER_CLUSTER", "default(2)")
 for name, extra in (("full", 0), ("skip_lo_mma", 1 << 30), ("no_sin", 1 << 31), ("skip_lo+no_sin", (1 << 30) | (1 << 31))):
     with torch.no_grad():
         film = R._film(inp["w"])
@@ -27,4 +29,4 @@ for name, extra in (("full", 0), ("skip_lo_mma", 1 << 30), ("no_sin", 1 << 31), 
                           flags_over=base | extra)
             b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-    print(f"{name:16s} {statistics.median(ts[2:]):.3f} ms")
+    print(f"cluster={cl:10s} {name:16s} {statistics.median(ts[2:]):.3f} ms")
