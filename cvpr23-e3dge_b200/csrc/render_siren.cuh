@@ -65,6 +65,9 @@ struct RenderArgs {
   float* p_rgb;
   float* p_feat;
   int with_view;  // 0: stop after the sdf head (sdf-only query)
+  // measurement aid (profiles/trace_render.py): when non-null, CTA 0 records clock64() stamps of the
+  // barrier hand-offs of its second tile: [0,128) compute warp, [128,256) MMA waits, [256,384) MMA issue
+  unsigned long long* trace;
 };
 
 

@@ -164,10 +164,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       const bool skip_lo = (a.p.flags & DBG_SKIP_LO_MMA) != 0;
       uint32_t stage = 0, phase = 0, pa = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
+        const bool tr = a.trace && blockIdx.x == 0 && t == 1;
         for (int l = 0; l < gemm_layers; ++l) {  // l-th GEMM of the tile = reference layer l+1
           const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256;
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&sm.a_ready[kb], pa);  // k-block kb of this layer's A operand is published
+            if (tr) a.trace[128 + l * 8 + kb] = clock64();
             tc::fence_after_thread_sync();
             const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
             const uint64_t dAl = tc::make_smem_desc_sw128(a_lo0 + kb * A_KBLOCK_BYTES);
@@ -190,6 +192,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
               }
               if (CL == 1) tc::mma_commit(&sm.empty[stage]);
               else tc::mma_commit_multicast(&sm.empty[stage], cl_mask);
+              if (tr) a.trace[256 + l * 16 + kb * 4 + tl] = clock64();
               if (++stage == TC_RING) {
                 stage = 0;
                 phase ^= 1;
@@ -323,6 +326,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       };
       const bool taps = (MODE == 0) && a.out.feats_taps && valid;
+      const bool tr = a.trace && blockIdx.x == 0 && slot == 1 && tid == 64;
+      if (tr) a.trace[0] = clock64();
 
       // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta'), 4 blocks ----
 #pragma unroll 1
@@ -347,6 +352,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
           if (taps) store_tap(0, n0, v);
         }
         publish(j);
+        if (tr) a.trace[1 + j] = clock64();
       }
 
       // ---- hidden layers 1..7: TMEM -> FiLM + sin -> next A operand, 64 channels at a time ----
@@ -354,6 +360,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
       for (int l = 1; l < 8; ++l) {
         mbar_wait(&sm.d_ready, pd);
         pd ^= 1;
+        if (tr) a.trace[l * 8] = clock64();
         tc::fence_after_thread_sync();
         const uint32_t dsrc = trow + (uint32_t)((l - 1) & 1) * 256;  // GEMM index l-1 -> TMEM half
         const bool last = (l == 7);
@@ -391,6 +398,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
             if (feed) store_a8(sm, m, n0, v);
           }
           if (feed) publish(j);
+          if (tr) a.trace[l * 8 + 1 + j] = clock64();
         }
         if (!feed) tc::fence_before_thread_sync();
       }
@@ -459,6 +467,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         // ---- view layer epilogue: + W_dir*viewdir, FiLM, sin; rgb head; weighted feature sum ----
         mbar_wait(&sm.d_ready, pd);
         pd ^= 1;
+        if (tr) a.trace[64] = clock64();
         tc::fence_after_thread_sync();
         const uint32_t dsrc = trow + 256u;  // GEMM index 7 -> TMEM half 1
         const float wrow = (MODE == 0 && valid) ? sm.wgt[m] : 0.f;
@@ -556,6 +565,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
                    pk[OFF_HEADB + 1 + c];
         }
       }
+      if (tr) a.trace[65] = clock64();
       compute_sync();  // shared memory is reused by the next tile
     }
   }
@@ -613,8 +623,11 @@ static int render_cluster_size() {
   return cached;
 }
 
-int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream) {
-  if (a.n_tiles <= 0) return E3_OK;
+int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
+  if (a_in.n_tiles <= 0) return E3_OK;
+  RenderArgs a = a_in;
+  if (const char* tp = getenv("E3DGE_RENDER_TRACE_PTR"))  // measurement aid, see RenderArgs::trace
+    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
   const int cl = render_cluster_size();
   if (mode == 0) {
     if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
