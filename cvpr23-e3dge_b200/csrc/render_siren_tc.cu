@@ -98,9 +98,12 @@ __device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float*
 // cluster has consumed it (tcgen05.commit multicast onto all CL `empty` barriers, count = CL).  This
 // divides the L2 -> SM traffic of the stream by CL and multiplies the bytes each SM has in flight,
 // which is what bounds the kernel at CL = 1 (profiles/r01e_whatif_render.txt).
+// wmap: 2-D tensor map over the pre-swizzled weight stream viewed as rows of 64 bf16 (128 B), box =
+// one 128-row tile, no hardware swizzle; use_wmap selects cp.async.bulk.tensor over the 1-D bulk copy.
 template <int MODE, int CL>
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
-siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
+siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ CUtensorMap wmap,
+                       const int use_wmap) {
   extern __shared__ uint8_t smem_raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -140,7 +143,9 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a) {
         for (int c = 0; c < per_tile; ++c) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&sm.full[stage], TC_TILE_BYTES);
-          if (CL == 1) {
+          if (CL == 1 && use_wmap) {
+            tc::tma_load_2d(sm.ring + stage * TC_TILE_BYTES, &wmap, &sm.full[stage], 0, c * 128);
+          } else if (CL == 1) {
             tma_bulk_g2s(sm.ring + stage * TC_TILE_BYTES, stream + (size_t)c * TC_TILE_BYTES,
                          TC_TILE_BYTES, &sm.full[stage]);
           } else {
@@ -600,7 +605,7 @@ static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
   // SMs cannot all be tiled by clusters of 4)
   static thread_local int max_clusters = 0;
   if (!max_clusters) {
-    cfg.gridDim = dim3(((sm_count() + CL - 1) / CL) * CL);
+    cfg.gridDim = dim3((sm_count() / CL) * CL);
     int n = 0;
     E3_CUDA(cudaOccupancyMaxActiveClusters(&n, fn, &cfg));
     max_clusters = n > 0 ? n : 1;
@@ -608,7 +613,19 @@ static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
   int clusters = (a.n_tiles + CL - 1) / CL;
   if (clusters > max_clusters) clusters = max_clusters;
   cfg.gridDim = dim3(clusters * CL);
-  E3_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+  // weight stream as a 2-D tensor: [8 layers * 16 tiles * 128 rows][64 bf16]
+  CUtensorMap wmap;
+  const uint64_t wdims[2] = {64, (uint64_t)8 * TC_TILES_PER_LAYER * 128};
+  const uint64_t wstr[1] = {128};
+  const uint32_t wbox[2] = {64, 128};
+  int rc = make_tensor_map_bf16(&wmap, a.packed + OFF_TC_STREAM, 2, wdims, wstr, wbox, /*swizzle128=*/false);
+  if (rc) return rc;
+  static int use_wmap = -1;
+  if (use_wmap < 0) {
+    const char* e = getenv("E3DGE_RENDER_WSTREAM");  // measurement aid: "bulk" | "tensor"
+    use_wmap = (e && e[0] == 'b') ? 0 : 1;
+  }
+  E3_CUDA(cudaLaunchKernelEx(&cfg, fn, a, wmap, use_wmap));
   return E3_OK;
 }
 
@@ -618,7 +635,7 @@ static int render_cluster_size() {
   if (!cached) {
     const char* e = getenv("E3DGE_RENDER_CLUSTER");
     const int v = e ? atoi(e) : 0;
-    cached = (v == 1 || v == 2 || v == 4) ? v : 2;
+    cached = (v == 1 || v == 2 || v == 4) ? v : 1;
   }
   return cached;
 }

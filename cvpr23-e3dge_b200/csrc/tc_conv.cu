@@ -34,7 +34,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box) {
+                         const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
   PFN_encodeTiled enc = get_encode_tiled();
   E3_REQUIRE(enc != nullptr, E3_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
   cuuint64_t gdim[5], gstr[5];
@@ -46,7 +46,8 @@ int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                   gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   E3_REQUIRE(r == CUDA_SUCCESS, E3_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return E3_OK;

@@ -165,6 +165,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 // bf16 tensor, innermost dim first; strides in bytes for dims 1..rank-1; 128B swizzle, zero OOB fill.
 int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box);
+                         const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
 
 }  // namespace e3
