@@ -10,7 +10,7 @@
 //     (h = hi + lo to 2^-17), K-major SWIZZLE_128B, 4 k-blocks x 16 KB each — written in place
 //     by the epilogue of the previous layer;
 //   * per layer D[128x256] (fp32 in TMEM) = h_hi*W_hi^T + h_lo*W_hi^T + h_hi*W_lo^T:
-//     96 tcgen05.mma 128x128x16 issued by one thread; the three-product split keeps the result
+//     48 tcgen05.mma 128x256x16 issued by one thread; the three-product split keeps the result
 //     fp32-faithful (measured 5e-5..1.5e-4 end to end vs 2..5e-2 for plain bf16 operands; the
 //     parity bar is 1e-3);
 //   * weights: 2 MB of pre-split, pre-swizzled bf16 tiles streamed from L2 by cp.async.bulk
@@ -65,6 +65,7 @@ struct SmemTC {
   uint32_t tmem_slot;
 };
 static_assert(sizeof(SmemTC) + 1024 <= 227 * 1024, "shared memory budget");
+static_assert(TC_RING == 4 && TC_TILES_PER_LAYER % 4 == 0, "stage pairing of the 256-row weight blocks");
 
 __device__ __forceinline__ void compute_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_COMPUTE) : "memory");
@@ -164,7 +165,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16_f32(128, 128);
+      const uint32_t idesc = tc::make_idesc_bf16_f32(128, 256);
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
       const bool skip_lo = (a.p.flags & DBG_SKIP_LO_MMA) != 0;
       uint32_t stage = 0, phase = 0, pa = 0;
@@ -178,27 +179,34 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             tc::fence_after_thread_sync();
             const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
             const uint64_t dAl = tc::make_smem_desc_sw128(a_lo0 + kb * A_KBLOCK_BYTES);
+            // Two adjacent ring stages hold the n-halves of one 256 x 64 weight block ((hi,n0),(hi,n1)
+            // then (lo,n0),(lo,n1); 16 tiles per layer and 4 stages keep the pairs aligned), so one
+            // 128x256x16 UMMA covers both halves: the A operand is read from shared memory once per
+            // 256 output columns instead of twice (shared-memory bandwidth bounds this kernel).
 #pragma unroll
-            for (int tl = 0; tl < 4; ++tl) {  // (hi,n0) (hi,n1) (lo,n0) (lo,n1)
-              const int is_lo = tl >> 1, nh = tl & 1;
+            for (int pr = 0; pr < 2; ++pr) {  // pr 0: W_hi block, pr 1: W_lo block
               mbar_wait(&sm.full[stage], phase);
+              mbar_wait(&sm.full[stage + 1], phase);
               tc::fence_after_thread_sync();
               const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
-              const uint32_t d = dcol + nh * 128;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t bk = tc::advance_desc_k(dB, ks);
-                if (!is_lo) {
-                  tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
-                  if (!skip_lo) tc::mma_bf16_ss(d, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+                if (pr == 0) {
+                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
+                  if (!skip_lo) tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAl, ks), bk, idesc, true);
                 } else if (!skip_lo) {
-                  tc::mma_bf16_ss(d, tc::advance_desc_k(dAh, ks), bk, idesc, true);
+                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, true);
                 }
               }
-              if (CL == 1) tc::mma_commit(&sm.empty[stage]);
-              else tc::mma_commit_multicast(&sm.empty[stage], cl_mask);
-              if (tr) a.trace[256 + l * 16 + kb * 4 + tl] = clock64();
-              if (++stage == TC_RING) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (CL == 1) tc::mma_commit(&sm.empty[stage + h]);
+                else tc::mma_commit_multicast(&sm.empty[stage + h], cl_mask);
+              }
+              if (tr) a.trace[256 + l * 16 + kb * 4 + pr * 2 + 1] = clock64();
+              stage += 2;
+              if (stage == TC_RING) {
                 stage = 0;
                 phase ^= 1;
               }
