@@ -511,6 +511,11 @@ class Generator(nn.Module):
             styles = [truncation_latent[0] + truncation * (s - truncation_latent[0]) for s in styles]
         return styles
 
+    def data_sample_forward(self, styles, cam_poses, focals, near=0.88, far=1.12, **kwargs):
+        """stylesdf_model.py:905-921."""
+        latent = self.styles_and_noise_forward(styles)
+        return self.renderer.sdf_sample_pass(cam_poses, focals, near, far, styles=latent[0], **kwargs)
+
     def init_forward(self, styles, cam_poses, focals, near=0.88, far=1.12):
         latent = self.styles_and_noise_forward(styles)
         return self.renderer.mlp_init_pass(cam_poses, focals, near, far, styles=latent[0])

@@ -541,6 +541,29 @@ class VolumeFeatureRenderer(nn.Module):
         out["mask"] = out["mask"].permute(0, 2, 3, 4, 1).contiguous()
         return out
 
+    def sdf_sample_pass(self, cam_poses, focal, near, far, styles, return_grad=False,
+                        merge_spatial_dim=True):
+        """sdf at stratified-jittered samples along the camera rays — volume_renderer.py:1760-1831.
+        (The reference's version dereferences an undefined `normalized_pts` (:1811) and cannot run;
+        this one returns what its docstring promises: box-normalised points [B,3,N] and sdf [B,1,N].)"""
+        if return_grad:
+            raise NotImplementedError("sdf gradients need the renderer backward (next milestone)")
+        B, dev = cam_poses.shape[0], cam_poses.device
+        rays_o, rays_d, _ = self.get_rays(focal, cam_poses)
+        nr = near.unsqueeze(-1) * torch.ones_like(rays_d[..., :1])
+        fr = far.unsqueeze(-1) * torch.ones_like(rays_d[..., :1])
+        z = nr * (1. - self.t_vals) + fr * self.t_vals
+        mids = .5 * (z[..., 1:] + z[..., :-1])
+        upper = torch.cat([mids, z[..., -1:]], -1)
+        lower = torch.cat([z[..., :1], mids], -1)
+        z = lower + (upper - lower) * torch.rand(z.shape, device=dev)
+        pts = rays_o.unsqueeze(3) + rays_d.unsqueeze(3) * z.unsqueeze(-1)
+        sdf = self.sdf_query(pts.reshape(B, -1, 3), styles)
+        normalized = self.grid_warper(pts)
+        if merge_spatial_dim:
+            return {"points": normalized.reshape(B, -1, 3).permute(0, 2, 1), "sdf": sdf.reshape(B, 1, -1)}
+        return {"points": normalized, "sdf": sdf.reshape(z.shape)}
+
     def mlp_init_pass(self, cam_poses, focal, near, far, styles=None):
         """Sphere-init pass: sdf at stratified-jittered samples and its target
         |p| - (far-near)/4 — volume_renderer.py:1833-1863."""

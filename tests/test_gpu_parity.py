@@ -459,3 +459,18 @@ def test_tuple_generator_truncation_mean_latent_and_perturbed_sampling():
     zs = ((o["points"] - o["rays_o"].unsqueeze(3)) / o["rays_d"].unsqueeze(3))[..., 2]
     assert (zs[..., 1:] > zs[..., :-1]).all() and zs.min() >= 0.88 - 1e-4 and zs.max() < 1.12 + 1e-4
     assert (o["hit_prob"].sum(3) - 1).abs().max().item() < 1e-5
+
+
+def test_sdf_sample_pass_matches_oracle_at_the_returned_points():
+    size, res, seed = 64, 8, 717
+    G, sd = _build(size, res, seed, "sharp", full_pipeline=False)
+    inp = P.make_inputs(seed, 2, 1, res, wplus=False)
+    z = torch.randn(2, 256, generator=torch.Generator().manual_seed(seed))
+    d = _cuda(inp)
+    with torch.no_grad():
+        out = G.data_sample_forward([z.cuda()], d["cam_poses"], d["focal"], d["near"], d["far"])
+        w = O.mapping_network(z, sd)
+        pts_world = out["points"].permute(0, 2, 1).cpu() * 0.12          # undo the box warp
+        ref = O.sdf_query(sd, pts_world, w)
+    assert out["points"].shape == (2, 3, res * res * 24) and out["sdf"].shape == (2, 1, res * res * 24)
+    assert rel_linf(out["sdf"].reshape(2, -1, 1).cpu(), ref) < TOL
