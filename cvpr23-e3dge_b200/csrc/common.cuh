@@ -137,6 +137,21 @@ __device__ __forceinline__ float sin_fast_accurate(float a) {
   return __int_as_float(__float_as_int(res) ^ (__float_as_int(jm) << 31));
 }
 
+// sin(x) = sin.approx (MUFU) of x reduced EXACTLY to [-pi, pi] by a 3-term Cody-Waite split of 2*pi.
+// On [-pi, pi] the hardware approximation has max abs error 2^-21.41 (3.6e-7, CUDA math API) and the
+// reduction keeps |x| up to ~1e3 inside that range without losing phase accuracy (the raw __sinf
+// range reduction would add |x| * 6e-8).  ~7 instructions, the transcendental on the otherwise idle
+// MUFU pipe.  Used by the tensor-core renderer, whose operands are quantised to hi+lo bf16 (2^-17
+// relative, 20x coarser than this error); the exact-fp32 renderer keeps the polynomial version.
+__device__ __forceinline__ float sin_mufu_reduced(float a) {
+  const float jm = fmaf(a, 0.159154943f, 12582912.0f);  // rint(a / 2pi) + 1.5 * 2^23
+  const float j = jm - 12582912.0f;
+  float r = fmaf(j, -6.28125f, a);
+  r = fmaf(j, -1.93500518798828125e-3f, r);
+  r = fmaf(j, -3.019915981956752e-7f, r);
+  return __sinf(r);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);

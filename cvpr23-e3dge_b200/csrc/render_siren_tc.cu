@@ -61,7 +61,7 @@ struct SmemTC {
   float rgb_part[4][3][TCM];
   float ray_o[3][TCM], ray_d[3][TCM];
   uint64_t full[TC_RING], empty[TC_RING];
-  uint64_t a_ready[5], d_ready;  // blocks 0,1,2 (64 ch), then the two 32-ch halves of block 3
+  uint64_t a_ready[4], d_ready;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(SmemTC) + 1024 <= 227 * 1024, "shared memory budget");
@@ -116,7 +116,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       mbar_init(&sm.empty[s], CL);
     }
 #pragma unroll
-    for (int j = 0; j < 5; ++j) mbar_init(&sm.a_ready[j], TC_COMPUTE_WARPS);
+    for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], TC_COMPUTE_WARPS);
     mbar_init(&sm.d_ready, 1);
     fence_mbar_init();
   }
@@ -183,68 +183,33 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             // then (lo,n0),(lo,n1); 16 tiles per layer and 4 stages keep the pairs aligned), so one
             // 128x256x16 UMMA covers both halves: the A operand is read from shared memory once per
             // 256 output columns instead of twice (shared-memory bandwidth bounds this kernel).
-            if (kb < 3) {
 #pragma unroll
-              for (int pr = 0; pr < 2; ++pr) {  // pr 0: W_hi block, pr 1: W_lo block
-                mbar_wait(&sm.full[stage], phase);
-                mbar_wait(&sm.full[stage + 1], phase);
-                tc::fence_after_thread_sync();
-                const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t bk = tc::advance_desc_k(dB, ks);
-                  if (pr == 0) {
-                    tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
-                    if (!skip_lo) tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAl, ks), bk, idesc, true);
-                  } else if (!skip_lo) {
-                    tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, true);
-                  }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  if (CL == 1) tc::mma_commit(&sm.empty[stage + h]);
-                  else tc::mma_commit_multicast(&sm.empty[stage + h], cl_mask);
-                }
-                if (tr) a.trace[256 + l * 16 + kb * 4 + pr * 2 + 1] = clock64();
-                stage += 2;
-                if (stage == TC_RING) {
-                  stage = 0;
-                  phase ^= 1;
-                }
-              }
-            } else {
-              // last k-block: its A operand is published in two 32-channel halves (a_ready[3], [4]); the
-              // k16 steps 0,1 of BOTH weight blocks are issued on the first half, so only 6 of its 12 UMMAs
-              // remain after the epilogue's final publish (the exposed tail of the layer).  All four ring
-              // stages are held through this k-block; the next layer's first tiles are not needed before
-              // its first epilogue block has been published anyway.
-#pragma unroll
-              for (int h = 0; h < 4; ++h) mbar_wait(&sm.full[h], phase);  // stage == 0 here
+            for (int pr = 0; pr < 2; ++pr) {  // pr 0: W_hi block, pr 1: W_lo block
+              mbar_wait(&sm.full[stage], phase);
+              mbar_wait(&sm.full[stage + 1], phase);
               tc::fence_after_thread_sync();
-              const uint64_t dBh = tc::make_smem_desc_sw128(smem_u32(sm.ring));
-              const uint64_t dBl = tc::make_smem_desc_sw128(smem_u32(sm.ring + 2 * TC_TILE_BYTES));
+              const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                if (half == 1) {
-                  mbar_wait(&sm.a_ready[4], pa);
-                  tc::fence_after_thread_sync();
-                }
-#pragma unroll
-                for (int ks = 2 * half; ks < 2 * half + 2; ++ks) {
-                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), tc::advance_desc_k(dBh, ks), idesc, true);
-                  if (!skip_lo) {
-                    tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAl, ks), tc::advance_desc_k(dBh, ks), idesc, true);
-                    tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), tc::advance_desc_k(dBl, ks), idesc, true);
-                  }
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bk = tc::advance_desc_k(dB, ks);
+                if (pr == 0) {
+                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
+                  if (!skip_lo) tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+                } else if (!skip_lo) {
+                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, true);
                 }
               }
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                if (CL == 1) tc::mma_commit(&sm.empty[h]);
-                else tc::mma_commit_multicast(&sm.empty[h], cl_mask);
+              for (int h = 0; h < 2; ++h) {
+                if (CL == 1) tc::mma_commit(&sm.empty[stage + h]);
+                else tc::mma_commit_multicast(&sm.empty[stage + h], cl_mask);
               }
-              if (tr) a.trace[256 + l * 16 + kb * 4 + 3] = clock64();
-              phase ^= 1;  // the whole ring went round once (stage stays 0)
+              if (tr) a.trace[256 + l * 16 + kb * 4 + pr * 2 + 1] = clock64();
+              stage += 2;
+              if (stage == TC_RING) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
           pa ^= 1;  // each a_ready[kb] completes exactly once per layer
@@ -259,8 +224,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     const int q = warp & 3;               // TMEM lane quarter this warp may read
     const int hw = (warp - 2) >> 2;       // which 16-column quarter of each 64-channel block (0..3)
     const int m = q * 32 + lane;          // tile row = TMEM lane
-    const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t trow = trow0 + hw * 16;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + hw * 16;
     const int S = (MODE == 0) ? P.n_samples : 1;
     const int HW = (MODE == 0) ? P.height * P.width : a.n_points;
     const float* pk = a.packed;
@@ -378,38 +342,31 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       const bool tr = a.trace && blockIdx.x == 0 && slot == 1 && tid == 64;
       if (tr) a.trace[0] = clock64();
 
-      // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta') ----
-      // blocks 0..2: 16 channels per thread; block 3: two sequential 32-channel halves, 8 per thread
-      auto layer0_8 = [&](int n0) {
-        float v[8];
-#pragma unroll
-        for (int i4 = 0; i4 < 2; ++i4) {
-          const int n = n0 + i4 * 4;
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + n));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + SW + n));
-          const float4 w2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + 2 * SW + n));
-          const float a4[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
-                               fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[i4 * 4 + i] = sin_fast_accurate(fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]));
-        }
-        store_a8(sm, m, n0, v);
-        if (taps) store_tap(0, n0, v);
-      };
+      // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta'), 4 blocks ----
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        layer0_8(j * 64 + hw * 16);
-        layer0_8(j * 64 + hw * 16 + 8);
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int n0 = j * 64 + hw * 16 + g8 * 8;
+          float v[8];
+#pragma unroll
+          for (int i4 = 0; i4 < 2; ++i4) {
+            const int n = n0 + i4 * 4;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + n));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + SW + n));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + 2 * SW + n));
+            const float a4[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
+                                 fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              v[i4 * 4 + i] = sin_mufu_reduced(fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]));
+          }
+          store_a8(sm, m, n0, v);
+          if (taps) store_tap(0, n0, v);
+        }
         publish(j);
         if (tr) a.trace[1 + j] = clock64();
       }
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        layer0_8(192 + half * 32 + hw * 8);
-        publish(3 + half);
-      }
-      if (tr) a.trace[4] = clock64();
 
       // ---- hidden layers 1..7: TMEM -> FiLM + sin -> next A operand, 64 channels at a time ----
       float sdf_acc = 0.f;
@@ -418,8 +375,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         pd ^= 1;
         if (tr) a.trace[l * 8] = clock64();
         tc::fence_after_thread_sync();
-        const uint32_t dsrc0 = trow0 + (uint32_t)((l - 1) & 1) * 256;  // GEMM index l-1 -> TMEM half
-        const uint32_t dsrc = dsrc0 + hw * 16;
+        const uint32_t dsrc = trow + (uint32_t)((l - 1) & 1) * 256;  // GEMM index l-1 -> TMEM half
         const bool last = (l == 7);
         const bool feed = !last || a.with_view;
         const float* la = nullptr;
@@ -428,45 +384,35 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           la = a.in.local_alpha + (samp0 + m) * SW;
           lb = a.in.local_beta + (samp0 + m) * SW;
         }
-        // FiLM + sin (+ sdf head, local texture FiLM, taps) for 8 channels, then into the next A operand
-        auto hidden_8 = [&](int n0, const float* acc8) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float arg = fmaf(sm.film[l][0][n0 + i], acc8[i], sm.film[l][1][n0 + i]);
-            v[i] = no_sin ? arg * 1e-3f : sin_fast_accurate(arg);
-          }
-          if (last) {
-            // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sdf_acc = fmaf(sm.wsig[n0 + i], v[i], sdf_acc);
-            if (la) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[i] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + i], 1.f), v[i]), lb[n0 + i]);
-            }
-          }
-          if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
-          if (feed) store_a8(sm, m, n0, v);
-        };
 #pragma unroll 1
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float acc[16];
           tc::tmem_ld_32x16(dsrc + j * 64, acc);
-          hidden_8(j * 64 + hw * 16, acc);
-          hidden_8(j * 64 + hw * 16 + 8, acc + 8);
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const int n0 = j * 64 + hw * 16 + g8 * 8;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
+              v[i] = no_sin ? arg * 1e-3f : sin_mufu_reduced(arg);
+            }
+            if (last) {
+              // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sdf_acc = fmaf(sm.wsig[n0 + i], v[i], sdf_acc);
+              if (la) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  v[i] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + i], 1.f), v[i]), lb[n0 + i]);
+              }
+            }
+            if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
+            if (feed) store_a8(sm, m, n0, v);
+          }
           if (feed) publish(j);
           if (tr) a.trace[l * 8 + 1 + j] = clock64();
         }
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {  // block 3 in two sequential 32-channel halves
-          float acc[8];
-          const int n0 = 192 + half * 32 + hw * 8;
-          tc::tmem_ld_32x8(dsrc0 + n0, acc);
-          hidden_8(n0, acc);
-          if (feed) publish(3 + half);
-        }
-        if (tr) a.trace[l * 8 + 4] = clock64();
         if (!feed) tc::fence_before_thread_sync();
       }
       sm.sdf_part[hw][m] = sdf_acc;
@@ -564,7 +510,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               pre = fmaf(e0[i], v0, pre);
               pre = fmaf(e1[i], v1, pre);
               pre = fmaf(e2[i], v2, pre);
-              const float f = sin_fast_accurate(fmaf(sm.film[8][0][n + i], pre, sm.film[8][1][n + i]));
+              const float f = sin_mufu_reduced(fmaf(sm.film[8][0][n + i], pre, sm.film[8][1][n + i]));
               c0 = fmaf(q0[i], f, c0);
               c1 = fmaf(q1[i], f, c1);
               c2 = fmaf(q2[i], f, c2);
