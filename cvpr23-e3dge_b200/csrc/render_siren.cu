@@ -70,6 +70,27 @@ __global__ void siren_pack_kernel(e3_siren_weights w, float* __restrict__ packed
     v = w.views_w[(r % SW) * 259 + 256 + r / SW];
   } else if (idx < OFF_TC_STREAM) {
     v = 0.f;  // alignment padding
+  } else if (idx >= OFF_TC_STREAM_BWD) {
+    // backward stream: tiles of W^T (rows = forward input k, contraction over forward output n)
+    const int e0 = (idx - OFF_TC_STREAM_BWD) * 2;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = e0 + h;
+      const int tile = e / (128 * 64), in_tile = e % (128 * 64);
+      const int kh = tile & 1, is_lo = (tile >> 1) & 1, nb = (tile >> 2) & 3, l = tile >> 4;
+      const int byte = in_tile * 2;
+      const int r = (byte >> 10) * 8 + ((byte >> 7) & 7);
+      const int chunk = ((byte >> 4) & 7) ^ (r & 7);
+      const int kk = chunk * 8 + ((byte >> 1) & 7);
+      const int k = kh * 128 + r, n = nb * 64 + kk;
+      const float wv = (l < 7) ? w.pts_w[l + 1][n * SW + k] : w.views_w[n * 259 + k];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+      const uint16_t u = is_lo ? __bfloat16_as_ushort(lo) : __bfloat16_as_ushort(hi);
+      bits |= (uint32_t)u << (16 * h);
+    }
+    v = __uint_as_float(bits);
   } else {
     // two bf16 per float slot of the tensor-core stream
     const int e0 = (idx - OFF_TC_STREAM) * 2;
@@ -654,13 +675,16 @@ extern "C" int e3_render_fwd(const void* packed, const e3_render_params* p, cons
   a.tiles_per_image = (hw + a.rays_per_tile - 1) / a.rays_per_tile;
   a.n_tiles = a.tiles_per_image * p->batch;
   a.with_view = 1;
+  E3_REQUIRE(!(ffma && out->bwd_stash), E3_ERR_UNSUPPORTED,
+             "e3_render_fwd: bwd_stash (training) needs the tensor-core renderer");
+  a.stash = out->bwd_stash;
   return ffma ? launch_render(a, 0, as_stream(stream)) : launch_render_tc(a, 0, as_stream(stream));
 }
 
-extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
-                                   const float* viewdirs, int batch, int n_points, float pts_scale,
-                                   float* sdf, float* raw_rgb, float* feat, uint32_t flags,
-                                   void* stream) {
+static int siren_points_fwd_impl(const void* packed, const float* film, const float* points,
+                                 const float* viewdirs, int batch, int n_points, float pts_scale,
+                                 float* sdf, float* raw_rgb, float* feat, uint32_t flags, float* stash,
+                                 void* stream) {
   E3_REQUIRE(batch >= 0 && n_points >= 0, E3_ERR_BAD_ARG, "e3_siren_points_fwd: negative size");
   if (batch == 0 || n_points == 0) return E3_OK;
   E3_REQUIRE(packed && film && points && sdf, E3_ERR_BAD_ARG, "e3_siren_points_fwd: null argument");
@@ -682,5 +706,23 @@ extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const 
   a.tiles_per_image = (n_points + tile_m - 1) / tile_m;
   a.n_tiles = a.tiles_per_image * batch;
   a.with_view = (raw_rgb || feat) ? 1 : 0;
+  a.stash = stash;
   return ffma ? launch_render(a, 1, as_stream(stream)) : launch_render_tc(a, 1, as_stream(stream));
+}
+
+extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
+                                   const float* viewdirs, int batch, int n_points, float pts_scale,
+                                   float* sdf, float* raw_rgb, float* feat, uint32_t flags,
+                                   void* stream) {
+  return siren_points_fwd_impl(packed, film, points, viewdirs, batch, n_points, pts_scale, sdf, raw_rgb, feat,
+                               flags, nullptr, stream);
+}
+
+extern "C" int e3_siren_points_fwd_train(const void* packed, const float* film, const float* points,
+                                         const float* viewdirs, int batch, int n_points, float pts_scale,
+                                         float* sdf, float* raw_rgb, float* feat, float* bwd_stash,
+                                         void* stream) {
+  E3_REQUIRE(bwd_stash || batch == 0 || n_points == 0, E3_ERR_BAD_ARG, "e3_siren_points_fwd_train: bwd_stash missing");
+  return siren_points_fwd_impl(packed, film, points, viewdirs, batch, n_points, pts_scale, sdf, raw_rgb, feat, 0,
+                               bwd_stash, stream);
 }

@@ -339,6 +339,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       };
       const bool taps = (MODE == 0) && a.out.feats_taps && valid;
+      // training: pre-sin phases of every FiLM layer for e3_render_bwd ([layer][channel][row])
+      float* stash = (a.stash && !dummy) ? a.stash + (size_t)tile * STASH_FLOATS_PER_TILE + m : nullptr;
       const bool tr = a.trace && blockIdx.x == 0 && slot == 1 && tid == 64;
       if (tr) a.trace[0] = clock64();
 
@@ -358,8 +360,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             const float a4[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
                                  fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              v[i4 * 4 + i] = sin_mufu_reduced(fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]));
+            for (int i = 0; i < 4; ++i) {
+              const float arg = fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]);
+              if (stash) stash[(size_t)(n + i) * TCM] = arg;
+              v[i4 * 4 + i] = sin_mufu_reduced(arg);
+            }
           }
           store_a8(sm, m, n0, v);
           if (taps) store_tap(0, n0, v);
@@ -395,6 +400,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
+              if (stash) stash[(size_t)(l * SW + n0 + i) * TCM] = arg;
               v[i] = no_sin ? arg * 1e-3f : sin_mufu_reduced(arg);
             }
             if (last) {
@@ -510,7 +516,9 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               pre = fmaf(e0[i], v0, pre);
               pre = fmaf(e1[i], v1, pre);
               pre = fmaf(e2[i], v2, pre);
-              const float f = sin_mufu_reduced(fmaf(sm.film[8][0][n + i], pre, sm.film[8][1][n + i]));
+              const float arg8 = fmaf(sm.film[8][0][n + i], pre, sm.film[8][1][n + i]);
+              if (stash) stash[(size_t)(8 * SW + n + i) * TCM] = arg8;
+              const float f = sin_mufu_reduced(arg8);
               c0 = fmaf(q0[i], f, c0);
               c1 = fmaf(q1[i], f, c1);
               c2 = fmaf(q2[i], f, c2);

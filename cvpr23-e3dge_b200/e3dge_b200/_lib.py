@@ -37,7 +37,20 @@ class RenderInputs(Structure):
 class RenderOutputs(Structure):
     _fields_ = [(n, _fp) for n in ("features", "thumb_rgb", "xyz", "mask", "depth", "sdf", "hit_prob",
                                    "visibility", "dists", "points", "rays_o", "rays_d", "viewdirs",
-                                   "raw_rgb", "feats_taps")]
+                                   "raw_rgb", "feats_taps", "bwd_stash")]
+
+
+class RenderSaved(Structure):
+    _fields_ = [(n, _fp) for n in ("stash", "sdf", "hit_prob", "raw_rgb")]
+
+
+class RenderGrads(Structure):
+    _fields_ = [(n, _fp) for n in ("d_features", "d_thumb_rgb", "d_xyz", "d_depth", "d_sdf",
+                                   "d_hit_prob")]
+
+
+class RenderBwdOutputs(Structure):
+    _fields_ = [(n, _fp) for n in ("d_film", "d_local_alpha", "d_local_beta", "d_points")]
 
 
 RENDER_STATIC_VIEWDIRS = 1
@@ -57,6 +70,15 @@ _PROTOTYPES = {
                               POINTER(RenderOutputs), _fp]),
     "e3_siren_points_fwd": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, c_uint32,
                                     _fp]),
+    "e3_siren_points_fwd_train": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, _fp,
+                                          _fp]),
+    "e3_render_stash_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "e3_render_bwd_scratch_bytes": (c_size_t, [c_int]),
+    "e3_render_bwd": (c_int, [_fp, POINTER(RenderParams), POINTER(RenderInputs), POINTER(RenderSaved),
+                              POINTER(RenderGrads), POINTER(RenderBwdOutputs), _fp, c_size_t, _fp]),
+    "e3_siren_points_bwd": (c_int, [_fp, _fp, c_int, c_int, c_float, _fp, c_int, c_int, _fp, _fp, _fp,
+                                    _fp, _fp, _fp, c_size_t, _fp]),
+    "e3_film_bwd": (c_int, [_fp, _fp, c_int, c_int, _fp, _fp]),
     "e3_fused_bias_act": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_int64, c_int64, c_int, c_int,
                                   c_float, c_float, _fp]),
     "e3_upfirdn2d": (c_int, [_fp, _fp, _fp] + [c_int] * 14 + [_fp]),
@@ -106,7 +128,8 @@ def exported_symbols():
 
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches)
 KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
-                    "e3_siren_points_fwd": 1, "e3_fused_bias_act": 1, "e3_upfirdn2d": 1,
+                    "e3_siren_points_fwd": 1, "e3_siren_points_fwd_train": 1, "e3_render_bwd": 3,
+                    "e3_siren_points_bwd": 3, "e3_film_bwd": 1, "e3_fused_bias_act": 1, "e3_upfirdn2d": 1,
                     "e3_modconv_weight_sq": 1, "e3_modconv_styles": 2, "e3_nchw_to_nhwc": 1,
                     "e3_nhwc_to_nchw": 1, "e3_conv_pack_weight": 1, "e3_styled_conv3x3_fwd": 2,
                     "e3_styled_conv3x3_up_fwd": 3, "e3_torgb_fwd": 1,

@@ -7,7 +7,13 @@ returned dict is ONE CUDA kernel (csrc/render_siren.cu) instead of ~150 ATen lau
 
 Not provided (SURVEY.md §8 out of scope / "next" rows): marching-cubes mesh extraction
 (`return_mesh`), the PIFu `netLocal` network itself (its output enters here as an explicit
-(alpha, beta) texture modulation), eikonal terms (need the backward kernels).
+(alpha, beta) texture modulation), second-order gradients (the eikonal terms are returned
+as values of the backward kernel, without a graph of their own).
+
+Training (encoders against the frozen generator, trainer.py:881-900): `_FilmFn`, `_RenderFn`
+and `_PointsFn` bind e3_film_bwd / e3_render_bwd / e3_siren_points_bwd, so gradients reach the
+w / w+ latents, the local texture modulation and explicit query points.  The generator's own
+parameters and the cameras receive no gradient.
 """
 import math
 
@@ -173,27 +179,123 @@ class _PackedSiren:
         return buf
 
 
-class _RenderFn(torch.autograd.Function):
-    """Forward = the fused kernel.  Backward kernels are the next milestone (SURVEY.md §7
-    step 7); until then a backward through the renderer fails loudly instead of silently
-    returning no gradient."""
+def _scratch(batch, dev):
+    lib = _lib.load()
+    n = lib.e3_render_bwd_scratch_bytes(batch)
+    return torch.empty(max(n // 4, 1), device=dev, dtype=torch.float32), n
+
+
+class _FilmFn(torch.autograd.Function):
+    """styles -> FiLM table [B,9,3,256] (e3_film_fwd) with its adjoint (e3_film_bwd)."""
 
     @staticmethod
-    def forward(ctx, renderer, styles, cam_poses, focal, near, far, z_jitter, local_mod, flags_over,
-                want_taps):
-        out = renderer._render_raw(styles, cam_poses, focal, near, far, z_jitter, local_mod,
-                                   flags_over, want_taps)
+    def forward(ctx, renderer, styles):
+        ctx.renderer, ctx.shape = renderer, tuple(styles.shape)
+        return renderer._film(styles)
+
+    @staticmethod
+    def backward(ctx, d_film):
+        lib = _lib.load()
+        shape = ctx.shape
+        b, spi = shape[0], (1 if len(shape) == 2 else shape[1])
+        d2 = d_film[:, :, :2].contiguous()
+        d_styles = torch.empty(b, spi, 256, device=d_film.device, dtype=torch.float32)
+        _lib.check(lib.e3_film_bwd(_lib.ptr(ctx.renderer.packed_weights()), _lib.ptr(d2), b, spi,
+                                   _lib.ptr(d_styles), _lib.cur_stream()), "e3_film_bwd")
+        return None, d_styles.reshape(shape)
+
+
+class _RenderFn(torch.autograd.Function):
+    """Forward = the fused kernel writing its backward stash; backward = e3_render_bwd.
+    Differentiable inputs: the FiLM table and the local texture modulation."""
+
+    DIFF = ("features", "gen_thumb_imgs", "xyz", "depth", "sdf", "hit_prob")
+
+    @staticmethod
+    def forward(ctx, renderer, film, local_alpha, local_beta, cam_poses, focal, near, far, z_jitter,
+                flags_over, want_taps):
+        local_mod = None if local_alpha is None else (local_alpha, local_beta)
+        out, call = renderer._render_raw(None, cam_poses, focal, near, far, z_jitter, local_mod,
+                                         flags_over, want_taps, film=film, train=True)
         names = list(out.keys())
-        ctx.names = names
-        ctx.mark_non_differentiable(*[out[k] for k in ("rays_o", "rays_d", "viewdirs", "mask")])
+        ctx.names, ctx.renderer, ctx.call = names, renderer, call
+        ctx.saved = {k: out[k] for k in ("sdf", "hit_prob", "raw_rgb")}
+        ctx.want_local = local_alpha is not None
+        ctx.mark_non_differentiable(*[out[k] for k in names if k not in _RenderFn.DIFF])
         renderer._last_names = names
         return tuple(out[k] for k in names)
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError(
-            "e3dge_b200: backward through the fused renderer is not implemented yet "
-            "(forward / inference path only in this round)")
+        import ctypes
+        lib = _lib.load()
+        call = ctx.call
+        g = {k: v for k, v in zip(ctx.names, grads)}
+        gin = [(_lib.as_f32c(g[k]) if g.get(k) is not None else None) for k in _RenderFn.DIFF]
+        film = call["film"]
+        B, dev = film.shape[0], film.device
+        d_film = torch.empty(B, 9, 2, 256, device=dev, dtype=torch.float32)
+        d_la = d_lb = None
+        if ctx.want_local and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+            d_la = torch.empty_like(call["la"])
+            d_lb = torch.empty_like(call["lb"])
+        scratch, nbytes = _scratch(B, dev)
+        saved = _lib.RenderSaved(_lib.ptr(call["stash"]), _lib.ptr(ctx.saved["sdf"]),
+                                 _lib.ptr(ctx.saved["hit_prob"]), _lib.ptr(ctx.saved["raw_rgb"]))
+        gr = _lib.RenderGrads(*[_lib.ptr(t) for t in gin])
+        bo = _lib.RenderBwdOutputs(_lib.ptr(d_film), _lib.ptr(d_la), _lib.ptr(d_lb), None)
+        _lib.check(lib.e3_render_bwd(_lib.ptr(ctx.renderer.packed_weights()), ctypes.byref(call["prm"]),
+                                     ctypes.byref(call["inp"]), ctypes.byref(saved), ctypes.byref(gr),
+                                     ctypes.byref(bo), _lib.ptr(scratch), nbytes, _lib.cur_stream()),
+                   "e3_render_bwd")
+        d_film3 = torch.zeros(B, 9, 3, 256, device=dev, dtype=torch.float32)
+        d_film3[:, :, :2] = d_film
+        return (None, d_film3, d_la, d_lb) + (None,) * 7
+
+
+class _PointsFn(torch.autograd.Function):
+    """FiLM-SIREN at explicit points with a backward (e3_siren_points_fwd_train / _bwd).
+    Differentiable inputs: the FiLM table and the points."""
+
+    @staticmethod
+    def forward(ctx, renderer, film, pts, viewdirs, with_view):
+        lib = _lib.load()
+        B, N = pts.shape[0], pts.shape[1]
+        dev = pts.device
+        sdf = torch.empty(B, N, device=dev, dtype=torch.float32)
+        rgb = torch.empty(B, N, 3, device=dev, dtype=torch.float32) if with_view else None
+        feat = torch.empty(B, N, 256, device=dev, dtype=torch.float32) if with_view else None
+        stash = torch.empty(max(lib.e3_render_stash_bytes(1, N, B) // 4, 1), device=dev,
+                            dtype=torch.float32)
+        scale = float(renderer.grid_warper.scale_factor)
+        _lib.check(lib.e3_siren_points_fwd_train(
+            _lib.ptr(renderer.packed_weights()), _lib.ptr(film), _lib.ptr(pts), _lib.ptr(viewdirs), B, N,
+            scale, _lib.ptr(sdf), _lib.ptr(rgb), _lib.ptr(feat), _lib.ptr(stash), _lib.cur_stream()),
+            "e3_siren_points_fwd_train")
+        ctx.renderer, ctx.film, ctx.stash, ctx.with_view, ctx.scale = renderer, film, stash, with_view, scale
+        ctx.dims = (B, N)
+        if with_view:
+            return sdf, rgb, feat
+        return sdf, None, None
+
+    @staticmethod
+    def backward(ctx, d_sdf, d_rgb, d_feat):
+        lib = _lib.load()
+        B, N = ctx.dims
+        dev = ctx.film.device
+        c = lambda t: _lib.as_f32c(t) if t is not None else None
+        d_sdf, d_rgb, d_feat = c(d_sdf), c(d_rgb), c(d_feat)
+        d_film = torch.empty(B, 9, 2, 256, device=dev, dtype=torch.float32)
+        d_pts = torch.empty(B, N, 3, device=dev, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        scratch, nbytes = _scratch(B, dev)
+        _lib.check(lib.e3_siren_points_bwd(
+            _lib.ptr(ctx.renderer.packed_weights()), _lib.ptr(ctx.film), B, N, ctx.scale,
+            _lib.ptr(ctx.stash), int(ctx.with_view), 0, _lib.ptr(d_sdf), _lib.ptr(d_rgb), _lib.ptr(d_feat),
+            _lib.ptr(d_film), _lib.ptr(d_pts), _lib.ptr(scratch), nbytes, _lib.cur_stream()),
+            "e3_siren_points_bwd")
+        d_film3 = torch.zeros(B, 9, 3, 256, device=dev, dtype=torch.float32)
+        d_film3[:, :, :2] = d_film
+        return None, d_film3, d_pts, None, None
 
 
 class VolumeFeatureRenderer(nn.Module):
@@ -297,7 +399,7 @@ class VolumeFeatureRenderer(nn.Module):
         return f
 
     def _render_raw(self, styles, cam_poses, focal, near, far, z_jitter=None, local_mod=None,
-                    flags_over=None, want_taps=False, film=None):
+                    flags_over=None, want_taps=False, film=None, train=False):
         import ctypes
         lib = _lib.load()
         dev = cam_poses.device
@@ -338,15 +440,26 @@ class VolumeFeatureRenderer(nn.Module):
         zj = _lib.as_f32c(z_jitter) if z_jitter is not None else None
         inp = _lib.RenderInputs(*[_lib.ptr(t) for t in (cam, focal_v, near_v, far_v, pix, pix, tv, zj,
                                                         sb, film, la, lb)])
+        stash = None
+        if train:
+            if self.backend != "tensor_cores":
+                raise RuntimeError("e3dge_b200: training (backward) needs backend='tensor_cores'")
+            stash = torch.empty(max(lib.e3_render_stash_bytes(S, n * n, B) // 4, 1), device=dev,
+                                dtype=torch.float32)
         outs = _lib.RenderOutputs(*[_lib.ptr(o[k]) for k in (
             "features", "gen_thumb_imgs", "xyz", "mask", "depth", "sdf", "hit_prob", "visibility",
             "dists", "points", "rays_o", "rays_d", "viewdirs", "raw_rgb")],
-            _lib.ptr(o["all_feats"]) if want_taps else None)
+            _lib.ptr(o["all_feats"]) if want_taps else None, _lib.ptr(stash))
         _lib.check(lib.e3_render_fwd(_lib.ptr(self.packed_weights()), ctypes.byref(prm),
                                      ctypes.byref(inp), ctypes.byref(outs), _lib.cur_stream()),
                    "e3_render_fwd")
         o["near"] = near_v.reshape(B, 1, 1, 1).expand(B, n, n, 1)
         o["far"] = far_v.reshape(B, 1, 1, 1).expand(B, n, n, 1)
+        if train:
+            # everything the backward call reads again (keeps the argument tensors alive)
+            call = dict(prm=prm, inp=inp, film=film, stash=stash, la=la, lb=lb,
+                        keep=(cam, focal_v, near_v, far_v, pix, tv, zj, sb))
+            return o, call
         return o
 
     def _make_z_jitter(self, near, far, B, dev):
@@ -399,6 +512,12 @@ class VolumeFeatureRenderer(nn.Module):
                 viewdirs = viewdirs.unsqueeze(self.samples_dim)
             viewdirs = viewdirs.expand(shp)
         vd = _lib.as_f32c(viewdirs).reshape(B, -1, 3)
+        if self._wants_grad(styles, inputs):
+            film = _FilmFn.apply(self, styles)
+            sdf, rgb, feat = _PointsFn.apply(self, film, pts, vd, not return_sdf_only)
+            if return_sdf_only:
+                return sdf.reshape(*shp[:-1], 1)
+            return torch.cat([rgb, sdf.unsqueeze(-1), feat], -1).reshape(*shp[:-1], 260)
         film = self._film(styles)
         sdf = torch.empty(B, N, device=pts.device, dtype=torch.float32)
         rgb = feat = None
@@ -421,6 +540,9 @@ class VolumeFeatureRenderer(nn.Module):
         lib = _lib.load()
         pts = _lib.as_f32c(points)
         B, N = pts.shape[0], pts.shape[1]
+        if self._wants_grad(styles, points):
+            film = _FilmFn.apply(self, styles)
+            return _PointsFn.apply(self, film, pts, None, False)[0].unsqueeze(-1)
         film = self._film(styles)
         sdf = torch.empty(B, N, device=pts.device, dtype=torch.float32)
         _lib.check(lib.e3_siren_points_fwd(_lib.ptr(self.packed_weights()), _lib.ptr(film),
@@ -429,6 +551,36 @@ class VolumeFeatureRenderer(nn.Module):
                                            None, self._point_flags(), _lib.cur_stream()),
                    "e3_siren_points_fwd")
         return sdf.unsqueeze(-1)
+
+    @staticmethod
+    def _wants_grad(*tensors):
+        return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+    @torch.no_grad()
+    def sdf_and_gradient(self, points, styles):
+        """(sdf [B,N,1], d sdf / d point [B,N,3]) — the value of get_eikonal_term
+        (volume_renderer.py:796-802): one sdf-only forward with stash + e3_siren_points_bwd seeded
+        with dL/dsdf = 1.  Returned without a graph (no second-order gradients)."""
+        lib = _lib.load()
+        pts = _lib.as_f32c(points.detach())
+        B, N = pts.shape[0], pts.shape[1]
+        dev = pts.device
+        film = self._film(styles.detach())
+        sdf = torch.empty(B, N, device=dev, dtype=torch.float32)
+        stash = torch.empty(max(lib.e3_render_stash_bytes(1, N, B) // 4, 1), device=dev, dtype=torch.float32)
+        scale = float(self.grid_warper.scale_factor)
+        _lib.check(lib.e3_siren_points_fwd_train(_lib.ptr(self.packed_weights()), _lib.ptr(film), _lib.ptr(pts),
+                                                 None, B, N, scale, _lib.ptr(sdf), None, None,
+                                                 _lib.ptr(stash), _lib.cur_stream()),
+                   "e3_siren_points_fwd_train")
+        d_film = torch.empty(B, 9, 2, 256, device=dev, dtype=torch.float32)
+        d_pts = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
+        scratch, nbytes = _scratch(B, dev)
+        _lib.check(lib.e3_siren_points_bwd(_lib.ptr(self.packed_weights()), _lib.ptr(film), B, N, scale,
+                                           _lib.ptr(stash), 0, 1, None, None, None, _lib.ptr(d_film),
+                                           _lib.ptr(d_pts), _lib.ptr(scratch), nbytes, _lib.cur_stream()),
+                   "e3_siren_points_bwd")
+        return sdf.unsqueeze(-1), d_pts
 
     def sample_uniform_grid(self, batch_size, num_sample_inout, device, styles):
         """volume_renderer.py:945-963."""
@@ -450,28 +602,39 @@ class VolumeFeatureRenderer(nn.Module):
         """volume_renderer.py:1666-1701."""
         if return_mesh:
             raise NotImplementedError("marching-cubes mesh extraction is out of scope (SURVEY.md §8f)")
-        if return_eikonal or kwargs.get("return_surface_eikonal", False):
-            raise NotImplementedError("eikonal terms need the renderer backward (next milestone)")
         B, dev = c2w.shape[0], c2w.device
         zj = self._make_z_jitter(near, far, B, dev) if (self.perturb and self.perturb > 0) else None
         local_mod = kwargs.get("local_tex_modulation")
         want_taps = bool(getattr(self.opt, "return_feats", False))
-        need_grad = torch.is_grad_enabled() and any(
-            torch.is_tensor(t) and t.requires_grad for t in (styles, c2w, focal))
+        need_grad = self._wants_grad(styles, *(local_mod or ()))
         if need_grad:
-            vals = _RenderFn.apply(self, styles, c2w, focal, near, far, zj, local_mod, None, want_taps)
+            film = _FilmFn.apply(self, styles)
+            la, lb = local_mod if local_mod is not None else (None, None)
+            vals = _RenderFn.apply(self, film, la, lb, c2w, focal, near, far, zj, None, want_taps)
             o = dict(zip(self._last_names, vals))
         else:
             o = self._render_raw(styles, c2w, focal, near, far, zj, local_mod, None, want_taps)
         n = self.out_im_res * self.spatial_ss
+        eik = surf_eik = None
+        if return_eikonal or kwargs.get("return_surface_eikonal", False):
+            # d sdf / d sample position (volume_renderer.py:855-856): values only, no graph
+            eik = self.sdf_and_gradient(o["points"].reshape(B, -1, 3), styles)[1].reshape(B, n, n, -1, 3)
+        if kwargs.get("return_surface_eikonal", False):
+            if getattr(self.opt, "use_integrated_surface_normal", False):
+                surf_eik = torch.sum(o["hit_prob"].detach() * eik, 3).unsqueeze(-2)  # :932-934
+            else:  # sdf gradient at the integrated surface point (:921-930)
+                xyz_pts = o["xyz"].detach().permute(0, 2, 3, 1).reshape(B, -1, 3)
+                surf_eik = self.sdf_and_gradient(xyz_pts, styles)[1].reshape(B, n, n, 1, 3)
+        if not return_eikonal:
+            eik = None
         out = {
             "rays_o": o["rays_o"], "rays_d": o["rays_d"], "dists": o["dists"], "near": o["near"],
-            "far": o["far"], "hit_prob": o["hit_prob"], "surface_eikonal_term": None,
+            "far": o["far"], "hit_prob": o["hit_prob"], "surface_eikonal_term": surf_eik,
             "points": o["points"], "sdf": o["sdf"] if self.return_sdf else None,
             "gen_thumb_imgs": o["gen_thumb_imgs"],
             "features": o["features"] if self.output_features else None,
             "mask": o["mask"] if self.return_xyz else None,
-            "xyz": o["xyz"] if self.return_xyz else None, "eikonal_term": None,
+            "xyz": o["xyz"] if self.return_xyz else None, "eikonal_term": eik,
             "depth": o["depth"] if self.return_xyz else None, "mesh": None, "shading_mesh": None,
             "debug_mesh": None, "viewdirs": o["viewdirs"],
         }
@@ -509,6 +672,9 @@ class VolumeFeatureRenderer(nn.Module):
                 shp = samples.shape
                 sdf = self.sdf_query(samples.reshape(shp[0], -1, 3), styles)
                 out[f"{k}_rec"] = sdf.reshape(*shp[:-1], 1)
+                if return_surface_eikonal and k == "xyz":  # :1945-1949
+                    out[f"{k}_rec_eikonal_term"] = self.sdf_and_gradient(
+                        samples.reshape(shp[0], -1, 3), styles)[1].reshape(*shp[:-1], 3)
         if sample_mode:
             out = self._sample_and_collate(out, styles)
             self.sample_mode = False
@@ -546,8 +712,6 @@ class VolumeFeatureRenderer(nn.Module):
         """sdf at stratified-jittered samples along the camera rays — volume_renderer.py:1760-1831.
         (The reference's version dereferences an undefined `normalized_pts` (:1811) and cannot run;
         this one returns what its docstring promises: box-normalised points [B,3,N] and sdf [B,1,N].)"""
-        if return_grad:
-            raise NotImplementedError("sdf gradients need the renderer backward (next milestone)")
         B, dev = cam_poses.shape[0], cam_poses.device
         rays_o, rays_d, _ = self.get_rays(focal, cam_poses)
         nr = near.unsqueeze(-1) * torch.ones_like(rays_d[..., :1])
@@ -558,11 +722,16 @@ class VolumeFeatureRenderer(nn.Module):
         lower = torch.cat([z[..., :1], mids], -1)
         z = lower + (upper - lower) * torch.rand(z.shape, device=dev)
         pts = rays_o.unsqueeze(3) + rays_d.unsqueeze(3) * z.unsqueeze(-1)
-        sdf = self.sdf_query(pts.reshape(B, -1, 3), styles)
         normalized = self.grid_warper(pts)
+        if return_grad:  # `sdf_norm` of :1824 = d sdf / d (world-space point)
+            sdf, grad = self.sdf_and_gradient(pts.reshape(B, -1, 3), styles)
+            extra = {"sdf_grad": grad.permute(0, 2, 1) if merge_spatial_dim else grad.reshape(*z.shape, 3)}
+        else:
+            sdf, extra = self.sdf_query(pts.reshape(B, -1, 3), styles), {}
         if merge_spatial_dim:
-            return {"points": normalized.reshape(B, -1, 3).permute(0, 2, 1), "sdf": sdf.reshape(B, 1, -1)}
-        return {"points": normalized, "sdf": sdf.reshape(z.shape)}
+            return {"points": normalized.reshape(B, -1, 3).permute(0, 2, 1), "sdf": sdf.reshape(B, 1, -1),
+                    **extra}
+        return {"points": normalized, "sdf": sdf.reshape(z.shape), **extra}
 
     def mlp_init_pass(self, cam_poses, focal, near, far, styles=None):
         """Sphere-init pass: sdf at stratified-jittered samples and its target

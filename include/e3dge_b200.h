@@ -131,6 +131,9 @@ typedef struct e3_render_outputs {
   float* raw_rgb;    /* [B,H,W,S,3] pre-sigmoid radiance (run_network(...)[..., :3]) */
   float* feats_taps; /* NULL or [4,B,H,W,S,256]: hidden states after layers 1,3,5,7
                         (rendering.return_feats, volume_renderer.py:172-193) */
+  float* bwd_stash;  /* NULL (inference), or e3_render_stash_bytes() bytes: what e3_render_bwd needs
+                        again (the pre-sin phase of every FiLM layer and sample; library-private
+                        layout).  Tensor-core renderer only. */
 } e3_render_outputs;
 
 /* Fused rays -> samples -> FiLM-SIREN x9 -> SDF->sigma -> alpha composite.
@@ -149,6 +152,66 @@ int e3_render_fwd(const void* packed, const e3_render_params* p, const e3_render
 int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
                         const float* viewdirs, int batch, int n_points, float pts_scale,
                         float* sdf, float* raw_rgb, float* feat, uint32_t flags, void* stream);
+/* Same, additionally writing the backward stash (e3_render_stash_bytes(1, n_points, batch) bytes)
+ * for e3_siren_points_bwd.  Tensor-core arithmetic only. */
+int e3_siren_points_fwd_train(const void* packed, const float* film, const float* points,
+                              const float* viewdirs, int batch, int n_points, float pts_scale,
+                              float* sdf, float* raw_rgb, float* feat, float* bwd_stash,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Backward of the renderer — what autograd gives the reference through
+ * VolumeFeatureRenderer.forward when the E3DGE runners train encoders against the frozen
+ * generator (trainer.py:881-900; e3dge_full_runner.py:219-306): gradients with respect to the
+ * FiLM table (-> w / w+ through e3_film_bwd), the local texture modulation and the sample
+ * positions (volume_renderer.py:796-802, get_eikonal_term).  The generator weights are
+ * frozen on this path: no weight gradients.  Camera parameters receive no gradient.
+ * ---------------------------------------------------------------------------------- */
+size_t e3_render_stash_bytes(int n_samples_per_ray, int rays_per_image, int batch);
+size_t e3_render_bwd_scratch_bytes(int batch);
+
+typedef struct e3_render_saved { /* results of the forward call, read again */
+  const float* stash;    /* e3_render_outputs.bwd_stash */
+  const float* sdf;      /* [B,H,W,S,1] */
+  const float* hit_prob; /* [B,H,W,S,1] */
+  const float* raw_rgb;  /* [B,H,W,S,3] */
+} e3_render_saved;
+
+typedef struct e3_render_grads { /* upstream gradients dL/d(output); any may be NULL (= zero) */
+  const float* d_features;  /* [B,256,H,W] */
+  const float* d_thumb_rgb; /* [B,3,H,W] */
+  const float* d_xyz;       /* [B,3,H,W] */
+  const float* d_depth;     /* [B,H,W,1,1] */
+  const float* d_sdf;       /* [B,H,W,S,1] */
+  const float* d_hit_prob;  /* [B,H,W,S,1] */
+} e3_render_grads;
+
+typedef struct e3_render_bwd_outputs {
+  float* d_film;        /* [B,9,2,256]: per FiLM layer dL/dgamma, dL/dbeta (required) */
+  float* d_local_alpha; /* NULL or [B,H,W,S,256] */
+  float* d_local_beta;  /* NULL or [B,H,W,S,256] */
+  float* d_points;      /* NULL or [B,H,W,S,3]: dL/d(world-space sample position) */
+} e3_render_bwd_outputs;
+
+/* p / in: exactly the arguments of the forward call.  scratch: e3_render_bwd_scratch_bytes(B). */
+int e3_render_bwd(const void* packed, const e3_render_params* p, const e3_render_inputs* in,
+                  const e3_render_saved* saved, const e3_render_grads* grads,
+                  const e3_render_bwd_outputs* out, void* scratch, size_t scratch_bytes,
+                  void* stream);
+
+/* Backward of e3_siren_points_fwd_train.  d_sdf [B,N], d_raw_rgb [B,N,3], d_feat [B,N,256] may be
+ * NULL; with_view = 0 runs the sdf-only graph (the forward call had raw_rgb == feat == NULL);
+ * unit_sdf_seed != 0 uses dL/dsdf = 1 for every point, so that d_points [B,N,3] is the spatial sdf
+ * gradient of get_eikonal_term (volume_renderer.py:796-802).  d_film [B,9,2,256] required. */
+int e3_siren_points_bwd(const void* packed, const float* film, int batch, int n_points,
+                        float pts_scale, const float* stash, int with_view, int unit_sdf_seed,
+                        const float* d_sdf, const float* d_raw_rgb, const float* d_feat,
+                        float* d_film, float* d_points, void* scratch, size_t scratch_bytes,
+                        void* stream);
+
+/* d_film [B,9,2,256] -> d_styles [B,styles_per_image,256] (adjoint of e3_film_fwd). */
+int e3_film_bwd(const void* packed, const float* d_film, int batch, int styles_per_image,
+                float* d_styles, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * StyleGAN2 ops — same semantics and argument order as the reference's extension ABI.

@@ -228,6 +228,42 @@ def run_ops_case(ref):
     return arrays
 
 
+GRAD_KEYS = ["gen_imgs", "gen_thumb_imgs", "features", "sdf", "xyz", "depth", "hit_prob"]
+
+
+def cotangent(key, shape):
+    """Deterministic upstream gradient for output `key` (no RNG: reproducible anywhere)."""
+    n = int(np.prod(shape))
+    k = GRAD_KEYS.index(key)
+    return torch.from_numpy(np.cos(np.arange(n, dtype=np.float64) * 0.37 + k).astype(np.float32)
+                            .reshape(shape))
+
+
+def run_grad_case(ref):
+    """Autograd of the REAL reference through G_pred_latents.forward: for every differentiable
+    output k, d <R_k, out_k> / d w+ (and / d decoder latent for the image), plus the eikonal
+    term of return_eikonal=True (volume_renderer.py:796-802, 855-856)."""
+    cfg = dict(size=32, res=8, n_samples=12, batch=2, seed=61, variant="sharp", wplus=True, ropt={})
+    torch.manual_seed(0)
+    G = build_generator(ref, cfg["size"], cfg["res"], cfg["n_samples"], cfg["seed"], cfg["variant"])
+    for p in G.parameters():
+        p.requires_grad_(False)
+    inp = P.make_inputs(cfg["seed"], cfg["batch"], G.decoder.n_latent, cfg["res"], wplus=True)
+    w = inp["w"].clone().requires_grad_(True)
+    wd = inp["w_dec"].clone().requires_grad_(True)
+    out = G([w, wd], inp["cam_poses"], inp["focal"], inp["near"], inp["far"], input_is_latent=True,
+            randomize_noise=False, return_xyz=True, return_sdf=True, return_eikonal=True)
+    arrays = {"eikonal_term": _np(out["eikonal_term"]).astype(np.float32)}
+    for k in GRAD_KEYS:
+        loss = (cotangent(k, tuple(out[k].shape)) * out[k]).sum()
+        gw, gd = torch.autograd.grad(loss, [w, wd], retain_graph=True, allow_unused=True)
+        arrays["dw." + k] = _np(gw).astype(np.float32)
+        if gd is not None and k == "gen_imgs":
+            arrays["dwdec." + k] = _np(gd).astype(np.float32)
+    arrays["config"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+    return arrays
+
+
 def main(argv):
     if not rh.reference_available():
         raise SystemExit("reference tree not available: cannot regenerate goldens")
@@ -239,6 +275,7 @@ def main(argv):
     jobs["small_localmod"] = lambda: run_localmod_case(ref)
     jobs["small_query_nfs"] = lambda: run_query_case(ref)
     jobs["ops"] = lambda: run_ops_case(ref)
+    jobs["small_grad"] = lambda: run_grad_case(ref)
     for name, job in jobs.items():
         if want and name not in want:
             continue

@@ -128,3 +128,38 @@ def test_ops_case():
     w = O.mapping_network(t("map.z"), sd)
     assert rel_linf(w, gold["map.w"]) < 1e-5
     assert rel_linf(O.decoder_mapping(w, sd), gold["map.w_dec"]) < 1e-5
+
+
+GRAD_KEYS = ["gen_imgs", "gen_thumb_imgs", "features", "sdf", "xyz", "depth", "hit_prob"]
+
+
+def cotangent(key, shape):
+    """The deterministic upstream gradients of oracle/gen_golden.py::cotangent."""
+    n = int(np.prod(shape))
+    k = GRAD_KEYS.index(key)
+    return torch.from_numpy(np.cos(np.arange(n, dtype=np.float64) * 0.37 + k).astype(np.float32)
+                            .reshape(shape))
+
+
+def test_gradients_and_eikonal_term_vs_reference_autograd():
+    """Autograd through the oracle == autograd through the real reference (fixture
+    small_grad): d<R_k, out_k>/d w+, d image / d decoder latent, and the eikonal term."""
+    gold, cfg = load_golden("small_grad")
+    torch.set_num_threads(8)
+    sd = synthetic_state_dict(cfg["size"], cfg["res"], cfg["seed"], cfg["variant"])
+    n_lat = decoder_layout(cfg["size"], cfg["res"])
+    inp = P.make_inputs(cfg["seed"], cfg["batch"], n_lat, cfg["res"], wplus=True)
+    w = inp["w"].clone().requires_grad_(True)
+    wd = inp["w_dec"].clone().requires_grad_(True)
+    out = O.generator_forward(sd, w, wd, inp["cam_poses"], inp["focal"], inp["near"], inp["far"],
+                              res=cfg["res"], n_samples=cfg["n_samples"])
+    for k in GRAD_KEYS:
+        loss = (cotangent(k, tuple(out[k].shape)) * out[k]).sum()
+        gw, gd = torch.autograd.grad(loss, [w, wd], retain_graph=True, allow_unused=True)
+        assert rel_linf(gw, gold["dw." + k]) < 2e-4, k
+        if k == "gen_imgs":
+            assert rel_linf(gd, gold["dwdec." + k]) < 2e-4
+    pts = out["points"].detach().clone().requires_grad_(True)
+    sdf = O.sdf_query(sd, pts.reshape(cfg["batch"], -1, 3), inp["w"])
+    eik = torch.autograd.grad(sdf.sum(), pts)[0]
+    assert rel_linf(eik, gold["eikonal_term"]) < 2e-4
