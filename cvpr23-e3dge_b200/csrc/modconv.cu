@@ -39,13 +39,19 @@ __global__ void weight_sq_kernel(const float* __restrict__ w, int n_oi, int kk, 
 
 // plain:    Wg[tap][ci][o]        = scale * W[o][ci][tap]
 // upsample: Wg[ci][tap*cout + o]  = scale * W[o][ci][tap]
+// mode 2 (backward of plain): Wg[tap][o][ci] = scale * W[o][ci][8 - tap]; mode 3: = scale * W[o][ci][tap]
 __global__ void conv_pack_kernel(const float* __restrict__ w, int cout, int cin, int upsample,
                                  float scale, float* __restrict__ wg) {
   const int64_t total = (int64_t)cout * cin * 9;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int o, ci, tap;
-    if (upsample) {
+    if (upsample >= 2) {
+      ci = (int)(idx % cin);
+      o = (int)((idx / cin) % cout);
+      tap = (int)(idx / ((int64_t)cout * cin));
+      if (upsample == 2) tap = 8 - tap;
+    } else if (upsample) {
       o = (int)(idx % cout);
       tap = (int)((idx / cout) % 9);
       ci = (int)(idx / ((int64_t)cout * 9));
@@ -424,6 +430,17 @@ __global__ void __launch_bounds__(256) pack_record_kernel(const float* __restric
   }
 }
 
+int conv_gemm_ffma_launch(const ConvGemmArgs& a, int taps, cudaStream_t stream) {
+  E3_REQUIRE(a.Cin % CG_BK == 0 && a.N % 4 == 0 && !a.planar, E3_ERR_UNSUPPORTED,
+             "CUDA-core conv: needs Cin %% 16 == 0 and N %% 4 == 0 (got Cin=%d N=%d)", a.Cin, a.N);
+  const int64_t M = (int64_t)a.B * a.H * a.W;
+  dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (a.N + CG_BN - 1) / CG_BN);
+  if (taps == 9) conv_gemm_ffma_kernel<9><<<grid, 256, 0, stream>>>(a);
+  else conv_gemm_ffma_kernel<1><<<grid, 256, 0, stream>>>(a);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
 static int grid_cap(int64_t blocks) {
   const int64_t cap = (int64_t)sm_count() * 32;
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
@@ -469,10 +486,14 @@ extern "C" size_t e3_conv_packed_bytes(int cout, int cin) {
 static inline const void* packed_bf16_part(const void* packed, int cout, int cin) {
   return static_cast<const char*>(packed) + (size_t)cout * cin * 9 * sizeof(float);
 }
+namespace e3 {
+const void* conv_packed_bf16_part(const void* packed, int cout, int cin) { return packed_bf16_part(packed, cout, cin); }
+}
 
 extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample,
                                    void* packed, void* stream) {
   E3_REQUIRE(weight && packed && cout > 0 && cin > 0, E3_ERR_BAD_ARG, "e3_conv_pack_weight: bad argument");
+  E3_REQUIRE(upsample >= 0 && upsample <= 3, E3_ERR_BAD_ARG, "e3_conv_pack_weight: layout %d outside 0..3", upsample);
   const float scale = 1.f / sqrtf((float)(cin * 9));
   conv_pack_kernel<<<grid_cap(((int64_t)cout * cin * 9 + 255) / 256), 256, 0, as_stream(stream)>>>(
       weight, cout, cin, upsample, scale, static_cast<float*>(packed));

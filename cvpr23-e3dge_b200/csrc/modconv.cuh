@@ -18,6 +18,10 @@ struct ConvGemmArgs {
   int64_t noise_bstride;
   const float* noise_w;   // [1]
   const float* act_bias;  // [N]
+  // 1: `x` is the parity-planar transposed-conv gradient [py][px][B][H+1][W+1][Cin] and tap (ky,kx)
+  // reads plane (ky&1, kx&1) at (y + (ky>>1), x + (kx>>1)) — the stride-2 gather of the up-conv
+  // backward as nine dense shifted reads (tensor-core path only, operands pre-split by the caller)
+  int planar;
 };
 
 bool tc_conv_supported(int B, int H, int W, int Cin, int N);
@@ -26,5 +30,12 @@ int tc_conv_pack_weight(const float* weight, int cout, int cin, int upsample, fl
                         void* packed_bf16, cudaStream_t stream);
 int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, void* split_scratch,
                    cudaStream_t stream);
+// same without the modulate+split pass: xs_hi / xs_lo are the caller's bf16 operand halves
+int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
+                            const void* xs_lo, cudaStream_t stream);
+// exact-fp32 implicit GEMM on the CUDA cores (modconv.cu); needs Cin % 16 == 0 and N % 4 == 0
+int conv_gemm_ffma_launch(const ConvGemmArgs& a, int taps, cudaStream_t stream);
+size_t tc_conv_planar_elems(int B, int H, int W, int C);  // elements of one planar operand half
+const void* conv_packed_bf16_part(const void* packed, int cout, int cin);
 
 }  // namespace e3

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(256) modulate_split_kernel(const float* __rest
 
 // K-major bf16 hi/lo weights:  plain    Wk[o][tap*cin + ci]        = scale * W[o][ci][tap]
 //                              upsample Wk[tap*cout + o][ci]        = scale * W[o][ci][tap]
+// backward (input gradients):  mode 2   Wk[ci][tap*cout + o]       = scale * W[o][ci][8 - tap]  (plain conv)
+//                              mode 3   Wk[ci][tap*cout + o]       = scale * W[o][ci][tap]      (up-conv, planar gather)
 __global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int cin, int upsample,
                                       float scale, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo) {
@@ -88,7 +90,13 @@ __global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int o, ci, tap;
-    if (upsample) {
+    if (upsample >= 2) {
+      const int k = (int)(idx % ((int64_t)9 * cout));
+      ci = (int)(idx / ((int64_t)9 * cout));
+      o = k % cout;
+      tap = k / cout;
+      if (upsample == 2) tap = 8 - tap;
+    } else if (upsample) {
       ci = (int)(idx % cin);
       const int n = (int)(idx / cin);
       o = n % cout;
@@ -176,12 +184,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tile_coords(tile, x0, y0, b0, n0);
         for (int kb = 0; kb < nkb; ++kb) {
           const int tap = kb / kpt, kc = kb - tap * kpt;
-          const int dx = (TAPS == 9) ? tap % 3 - 1 : 0, dy = (TAPS == 9) ? tap / 3 - 1 : 0;
+          int dx = (TAPS == 9) ? tap % 3 - 1 : 0, dy = (TAPS == 9) ? tap / 3 - 1 : 0, bc = b0;
+          if (TAPS == 9 && a.planar) {  // tap (ky,kx) -> plane (ky&1, kx&1), shift (ky>>1, kx>>1)
+            const int ky = tap / 3, kx = tap % 3;
+            dx = kx >> 1, dy = ky >> 1, bc = ((ky & 1) * 2 + (kx & 1)) * a.B + b0;
+          }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
           uint8_t* st = smem + stage * TC_STAGE_BYTES;
-          tc::tma_load_4d(st, &tmA_hi, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
-          tc::tma_load_4d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, b0);
+          tc::tma_load_4d(st, &tmA_hi, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, bc);
+          tc::tma_load_4d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, bc);
           tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[stage], tap * a.Cin + kc * TC_BK, n0);
           tc::tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[stage], tap * a.Cin + kc * TC_BK, n0);
           if (++stage == TC_STAGES) {
@@ -296,6 +308,8 @@ int tc_conv_pack_weight(const float* weight, int cout, int cin, int upsample, fl
   return E3_OK;
 }
 
+size_t tc_conv_planar_elems(int B, int H, int W, int C) { return (size_t)4 * B * (H + 1) * (W + 1) * C; }
+
 // a: x, s, out, B, H, W, Cin, N, epilogue fields filled by the caller; a.wg is unused here.
 int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, void* split_scratch,
                    cudaStream_t stream) {
@@ -312,6 +326,15 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
     modulate_split_kernel<<<blocks, 256, 0, stream>>>(a.x, a.s, xs_hi, xs_lo, nv, a.H * a.W, a.Cin);
     E3_CUDA(cudaGetLastError());
   }
+  return tc_conv_launch_presplit(a, taps, packed_bf16, xs_hi, xs_lo, stream);
+}
+
+int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
+                            const void* xs_lo, cudaStream_t stream) {
+  E3_REQUIRE(tc_conv_supported(a.B, a.H, a.W, a.Cin, a.N), E3_ERR_UNSUPPORTED,
+             "tensor-core conv: unsupported shape B=%d H=%d W=%d Cin=%d N=%d (needs power-of-two "
+             "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0)", a.B, a.H, a.W, a.Cin, a.N);
+  E3_REQUIRE(!a.planar || taps == 9, E3_ERR_BAD_ARG, "tensor-core conv: planar operands need 9 taps");
   TcTile t;
   t.bw = a.W < 128 ? a.W : 128;
   t.bh = (128 / t.bw) < a.H ? (128 / t.bw) : a.H;
@@ -324,8 +347,10 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
   const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(packed_bf16);
   const __nv_bfloat16* w_lo = w_hi + (size_t)a.N * K;
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  const uint64_t adims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
-  const uint64_t astr[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+  // planar operand: [4 planes * B][H+1][W+1][Cin]
+  const uint64_t aw = a.planar ? a.W + 1 : a.W, ah = a.planar ? a.H + 1 : a.H, ab = a.planar ? 4 * a.B : a.B;
+  const uint64_t adims[4] = {(uint64_t)a.Cin, aw, ah, ab};
+  const uint64_t astr[3] = {(uint64_t)a.Cin * 2, aw * a.Cin * 2, ah * aw * a.Cin * 2};
   const uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)t.bw, (uint32_t)t.bh, (uint32_t)t.bb};
   const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)a.N};
   const uint64_t bstr[1] = {(uint64_t)K * 2};

@@ -126,8 +126,10 @@ class _PackedConv:
         self.key = None
         self.wp = self.wsq = None
 
-    def get(self, weight, upsample):
-        key = (weight.data_ptr(), weight._version, bool(upsample))
+    def get(self, weight, layout):
+        """layout: 0 plain / 1 upsampling forward, 2 / 3 their backward images (E3_CONV_PACK_*)."""
+        layout = int(layout)
+        key = (weight.data_ptr(), weight._version, layout)
         if key == self.key:
             return self.wp, self.wsq
         lib = _lib.load()
@@ -140,7 +142,7 @@ class _PackedConv:
         if k == 3:
             wp = torch.empty(lib.e3_conv_packed_bytes(cout, cin) // 4, device=w.device,
                              dtype=torch.float32)
-            _lib.check(lib.e3_conv_pack_weight(_lib.ptr(w), cout, cin, int(bool(upsample)),
+            _lib.check(lib.e3_conv_pack_weight(_lib.ptr(w), cout, cin, layout,
                                                _lib.ptr(wp), _lib.cur_stream()),
                        "e3_conv_pack_weight")
         self.key, self.wp, self.wsq = key, wp, wsq
@@ -170,23 +172,93 @@ def _to_nchw(x):
     return y
 
 
-class _NoGradYet(torch.autograd.Function):
-    """Marks a kernel output as depending on `deps`; backward fails loudly (forward-only round)."""
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
+def _latent_grad(conv, ds, dd, s, d):
+    """(ds, dd) -> dlatent [B,512] (e3_modconv_styles_bwd)."""
+    lib = _lib.load()
+    b = ds.shape[0]
+    _, wsq = conv._packed.get(conv.weight, int(conv.upsample))
+    dlat = torch.empty(b, 512, device=ds.device, dtype=torch.float32)
+    _lib.check(lib.e3_modconv_styles_bwd(_lib.ptr(ds), _lib.ptr(dd), _lib.ptr(s), _lib.ptr(d),
+                                         _lib.ptr(wsq), _lib.ptr(_lib.as_f32c(conv.modulation.weight.detach())),
+                                         b, conv.in_channel, conv.out_channel, conv.kernel_size,
+                                         _lib.ptr(dlat), _lib.cur_stream()), "e3_modconv_styles_bwd")
+    return dlat
+
+
+class _StyledConvFn(torch.autograd.Function):
+    """StyledConv / bare ModulatedConv2d on NHWC tensors with its backward
+    (e3_styled_conv3x3_bwd + e3_modconv_styles_bwd): gradients for the input and the latent."""
 
     @staticmethod
-    def forward(ctx, out, what, *deps):
-        ctx.what = what
-        return out.view_as(out)
+    def forward(ctx, conv, x, latent, noise, noise_w, act_bias):
+        y, saved = _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias, want_saved=True)
+        ctx.conv, ctx.saved = conv, saved
+        ctx.save_for_backward(x, y)
+        return y
 
     @staticmethod
-    def backward(ctx, grad):
-        raise NotImplementedError(f"e3dge_b200: backward of {ctx.what} is not implemented yet")
+    def backward(ctx, dy):
+        lib = _lib.load()
+        conv, (s, d, has_d, noise, nstride, noise_w, act_bias) = ctx.conv, ctx.saved
+        x, y = ctx.saved_tensors
+        b, h, w, cin = x.shape
+        cout, up = conv.out_channel, int(conv.upsample)
+        dy = _lib.as_f32c(dy)
+        wp, _ = conv._packed_bwd.get(conv.weight, 2 + up)
+        dx = torch.empty_like(x)
+        ds = torch.empty(b, cin, device=x.device, dtype=torch.float32)
+        dd = torch.empty(b, cout, device=x.device, dtype=torch.float32) if has_d else None
+        nbytes = lib.e3_styled_conv_bwd_scratch_bytes(b, h, w, cin, cout, up)
+        scratch = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
+        _lib.check(lib.e3_styled_conv3x3_bwd(
+            _lib.ptr(dy), _lib.ptr(y), _lib.ptr(x), _lib.ptr(wp), _lib.ptr(s), _lib.ptr(d), _lib.ptr(noise),
+            nstride, _lib.ptr(noise_w), _lib.ptr(act_bias), _lib.ptr(dx), _lib.ptr(ds), _lib.ptr(dd), b, h, w,
+            cin, cout, up, _lib.ptr(scratch), nbytes, CONV_BACKENDS[conv.backend], _lib.cur_stream()),
+            "e3_styled_conv3x3_bwd")
+        dlat = _latent_grad(conv, ds, dd, s, d) if ctx.needs_input_grad[2] else None
+        return None, dx, dlat, None, None, None
 
 
-def _guard(out, what, *deps):
-    if torch.is_grad_enabled() and any(torch.is_tensor(d) and d.requires_grad for d in deps):
-        return _NoGradYet.apply(out, what, *[d for d in deps if torch.is_tensor(d)])
-    return out
+class _ToRGBFn(torch.autograd.Function):
+    """ToRGB on an NHWC input with its backward (e3_torgb_bwd; the skip gradient is the
+    e3_upfirdn2d adjoint of the FIR upsampling)."""
+
+    @staticmethod
+    def forward(ctx, conv, x, latent, bias, skip, upsample_skip, up_kernel):
+        rgb, s = _torgb_nhwc(conv, x, latent, bias, skip, upsample_skip, want_saved=True)
+        ctx.conv, ctx.s = conv, s
+        ctx.save_for_backward(x)
+        ctx.has_skip, ctx.upsample_skip, ctx.up_kernel = skip is not None, bool(upsample_skip), up_kernel
+        return rgb
+
+    @staticmethod
+    def backward(ctx, drgb):
+        lib = _lib.load()
+        conv, s = ctx.conv, ctx.s
+        x, = ctx.saved_tensors
+        b, h, w, cin = x.shape
+        drgb = _lib.as_f32c(drgb)
+        dx = torch.empty_like(x)
+        ds = torch.empty(b, cin, device=x.device, dtype=torch.float32)
+        nbytes = lib.e3_torgb_bwd_scratch_bytes(b, cin)
+        scratch = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
+        wt = _lib.as_f32c(conv.weight.detach().reshape(3, cin))
+        _lib.check(lib.e3_torgb_bwd(_lib.ptr(drgb), _lib.ptr(x), _lib.ptr(wt), _lib.ptr(s), _lib.ptr(dx),
+                                    _lib.ptr(ds), b, h, w, cin, _lib.ptr(scratch), nbytes, _lib.cur_stream()),
+                   "e3_torgb_bwd")
+        dlat = _latent_grad(conv, ds, None, s, None) if ctx.needs_input_grad[2] else None
+        dskip = None
+        if ctx.has_skip and ctx.needs_input_grad[4]:
+            if ctx.upsample_skip:  # adjoint of upfirdn2d(up=2, pad=(2,1)): down=2, pad=(1,1), flipped kernel
+                with torch.no_grad():
+                    dskip = upfirdn2d(drgb, torch.flip(ctx.up_kernel, [0, 1]), up=1, down=2, pad=(1, 1))
+            else:
+                dskip = drgb
+        return None, dx, dlat, None, dskip, None, None
 
 
 class ModulatedConv2d(nn.Module):
@@ -220,6 +292,7 @@ class ModulatedConv2d(nn.Module):
         # "fp32" / "tensor_cores" force one of them (include/e3dge_b200.h E3_CONV_*)
         self.backend = "auto"
         self._packed = _PackedConv()
+        self._packed_bwd = _PackedConv()
 
     def styles(self, latent):
         """s [B,cin] and (if demodulating) d [B,cout] for latent [B,512] (may be a strided
@@ -230,7 +303,7 @@ class ModulatedConv2d(nn.Module):
         if latent.shape[-1] != 512 or self.modulation.weight.shape[1] != 512:
             raise NotImplementedError("decoder style_dim must be 512")
         b = latent.shape[0]
-        _, wsq = self._packed.get(self.weight, self.upsample)
+        _, wsq = self._packed.get(self.weight, int(self.upsample))
         s = torch.empty(b, self.in_channel, device=latent.device, dtype=torch.float32)
         d = torch.empty(b, self.out_channel, device=latent.device,
                         dtype=torch.float32) if self.demodulate else None
@@ -252,21 +325,56 @@ class ModulatedConv2d(nn.Module):
             if self.out_channel != 3 or self.demodulate:
                 raise NotImplementedError("1x1 ModulatedConv2d is supported as ToRGB (3 outputs, "
                                           "no demodulation)")
-            return _torgb_nhwc(self, _to_nhwc(input), style, zero_b, None, False)
-        y = _styled_conv_nhwc(self, _to_nhwc(input), style, None, None, None)
-        return _guard(_to_nchw(y), "ModulatedConv2d", input, style)
+            return _torgb_apply(self, _nhwc(input), style, zero_b, None, False, None)
+        return _nchw(_styled_conv_apply(self, _nhwc(input), style, None, None, None))
 
 
-def _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias):
+class _Permute(torch.autograd.Function):
+    """NCHW <-> NHWC through the transpose kernels; the adjoint is the opposite transpose."""
+
+    @staticmethod
+    def forward(ctx, x, to_nhwc):
+        ctx.to_nhwc = to_nhwc
+        return _to_nhwc(x) if to_nhwc else _to_nchw(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _lib.as_f32c(g)
+        return (_to_nchw(g) if ctx.to_nhwc else _to_nhwc(g)), None
+
+
+def _nhwc(x):
+    return _Permute.apply(x, True) if _wants_grad(x) else _to_nhwc(x)
+
+
+def _nchw(x):
+    return _Permute.apply(x, False) if _wants_grad(x) else _to_nchw(x)
+
+
+def _styled_conv_apply(conv, x, latent, noise, noise_w, act_bias):
+    if _wants_grad(x, latent):
+        return _StyledConvFn.apply(conv, x, latent, noise, noise_w, act_bias)
+    return _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias)
+
+
+def _torgb_apply(conv, x, latent, bias, skip, upsample_skip, up_kernel):
+    if _wants_grad(x, latent, skip):
+        return _ToRGBFn.apply(conv, x, latent, bias, skip, upsample_skip, up_kernel)
+    return _torgb_nhwc(conv, x, latent, bias, skip, upsample_skip)
+
+
+def _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias, want_saved=False):
     """x [B,H,W,cin] NHWC -> StyledConv output [B,H',W',cout] NHWC.
     act_bias None = bare modulated conv (no noise / bias / activation)."""
     lib = _lib.load()
     b, h, w, cin = x.shape
     cout, up = conv.out_channel, conv.upsample
-    s, d = conv.styles(latent)
+    x = _lib.as_f32c(x.detach())
+    s, d = conv.styles(latent.detach())
+    has_d = d is not None
     if d is None:
         d = torch.ones(b, cout, device=x.device, dtype=torch.float32)
-    wp, _ = conv._packed.get(conv.weight, up)
+    wp, _ = conv._packed.get(conv.weight, int(up))
     oh, ow = (2 * h, 2 * w) if up else (h, w)
     nstride = 0
     if act_bias is not None:
@@ -284,13 +392,16 @@ def _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias):
             _lib.ptr(noise_w), _lib.ptr(act_bias), _lib.ptr(y), b, h, w, cin, cout,
             _lib.ptr(scratch), nbytes, CONV_BACKENDS[conv.backend], _lib.cur_stream())
     _lib.check(fn(*args), "e3_styled_conv3x3_up_fwd" if up else "e3_styled_conv3x3_fwd")
+    if want_saved:
+        return y, (s, d, has_d, noise, nstride, noise_w, act_bias)
     return y
 
 
-def _torgb_nhwc(conv, x, latent, bias, skip, upsample_skip):
+def _torgb_nhwc(conv, x, latent, bias, skip, upsample_skip, want_saved=False):
     lib = _lib.load()
     b, h, w, cin = x.shape
-    s, _ = conv.styles(latent)
+    x = _lib.as_f32c(x.detach())
+    s, _ = conv.styles(latent.detach())
     rgb = torch.empty(b, 3, h, w, device=x.device, dtype=torch.float32)
     wt = _lib.as_f32c(conv.weight.detach().reshape(3, cin))
     sk = _lib.as_f32c(skip) if skip is not None else None
@@ -298,6 +409,8 @@ def _torgb_nhwc(conv, x, latent, bias, skip, upsample_skip):
                                 _lib.ptr(_lib.as_f32c(bias.detach().reshape(3))), _lib.ptr(sk),
                                 int(bool(upsample_skip)), _lib.ptr(rgb), b, h, w, cin,
                                 _lib.cur_stream()), "e3_torgb_fwd")
+    if want_saved:
+        return rgb, s
     return rgb
 
 
@@ -340,11 +453,10 @@ class StyledConv(nn.Module):
         if noise is None:  # fresh noise per call (stylesdf_model.py:461-462)
             oh, ow = (2 * h, 2 * w) if self.conv.upsample else (h, w)
             noise = torch.empty(b, 1, oh, ow, device=x.device).normal_()
-        return _styled_conv_nhwc(self.conv, x, style, noise, self.noise.weight, self.activate.bias)
+        return _styled_conv_apply(self.conv, x, style, noise, self.noise.weight, self.activate.bias)
 
     def forward(self, input, style, noise=None, transform=None, mesh_path=None):
-        y = _to_nchw(self.forward_nhwc(_to_nhwc(input), style, noise))
-        return _guard(y, "StyledConv", input, style)
+        return _nchw(self.forward_nhwc(_nhwc(input), style, noise))
 
 
 class ToRGB(nn.Module):
@@ -359,10 +471,11 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
     def forward_nhwc(self, x, style, skip=None):
-        return _torgb_nhwc(self.conv, x, style, self.bias, skip, bool(self.upsample))
+        up = bool(self.upsample)
+        return _torgb_apply(self.conv, x, style, self.bias, skip, up, self.upsample.kernel if up else None)
 
     def forward(self, input, style, skip=None):
-        return _guard(self.forward_nhwc(_to_nhwc(input), style, skip), "ToRGB", input, style, skip)
+        return self.forward_nhwc(_nhwc(input), style, skip)
 
 
 class Decoder(nn.Module):
@@ -451,7 +564,7 @@ class Decoder(nn.Module):
                                                       truncation_latent, input_is_latent,
                                                       randomize_noise)
         latent = _lib.as_f32c(latent)
-        x = _to_nhwc(features)
+        x = _nhwc(features)
         out = self.conv1.forward_nhwc(x, latent[:, 0], noise[0])
         skip = self.to_rgb1.forward_nhwc(out, latent[:, 1], rgbd_in)
         i = 1
@@ -461,8 +574,7 @@ class Decoder(nn.Module):
             out = conv2.forward_nhwc(out, latent[:, i + 1], noise2)
             skip = to_rgb.forward_nhwc(out, latent[:, i + 2], skip)
             i += 2
-        image = _guard(skip, "Decoder", features, latent)
-        return image, (latent if return_latents else None)
+        return skip, (latent if return_latents else None)
 
 
 class Generator(nn.Module):

@@ -219,7 +219,9 @@ class _RenderFn(torch.autograd.Function):
                                          flags_over, want_taps, film=film, train=True)
         names = list(out.keys())
         ctx.names, ctx.renderer, ctx.call = names, renderer, call
-        ctx.saved = {k: out[k] for k in ("sdf", "hit_prob", "raw_rgb")}
+        # outputs go through save_for_backward (a plain attribute would tie them to the graph node
+        # in a reference cycle and keep the multi-GB stash alive until the cyclic GC runs)
+        ctx.save_for_backward(out["sdf"], out["hit_prob"], out["raw_rgb"])
         ctx.want_local = local_alpha is not None
         ctx.mark_non_differentiable(*[out[k] for k in names if k not in _RenderFn.DIFF])
         renderer._last_names = names
@@ -240,8 +242,8 @@ class _RenderFn(torch.autograd.Function):
             d_la = torch.empty_like(call["la"])
             d_lb = torch.empty_like(call["lb"])
         scratch, nbytes = _scratch(B, dev)
-        saved = _lib.RenderSaved(_lib.ptr(call["stash"]), _lib.ptr(ctx.saved["sdf"]),
-                                 _lib.ptr(ctx.saved["hit_prob"]), _lib.ptr(ctx.saved["raw_rgb"]))
+        sv_sdf, sv_hit, sv_rgb = ctx.saved_tensors
+        saved = _lib.RenderSaved(_lib.ptr(call["stash"]), _lib.ptr(sv_sdf), _lib.ptr(sv_hit), _lib.ptr(sv_rgb))
         gr = _lib.RenderGrads(*[_lib.ptr(t) for t in gin])
         bo = _lib.RenderBwdOutputs(_lib.ptr(d_film), _lib.ptr(d_la), _lib.ptr(d_lb), None)
         _lib.check(lib.e3_render_bwd(_lib.ptr(ctx.renderer.packed_weights()), ctypes.byref(call["prm"]),

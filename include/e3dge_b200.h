@@ -308,6 +308,51 @@ int e3_torgb_fwd(const float* x, const float* weight, const float* s, const floa
                  int cin, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Decoder backward — what autograd gives the reference through Decoder.forward
+ * (stylesdf_model.py:742-797) when image losses are back-propagated into the encoders
+ * (trainer.py:881-900): gradients with respect to the layer input and the layer's latent.
+ * The generator weights are frozen on this path: no weight / bias / noise-strength gradients.
+ * ---------------------------------------------------------------------------------- */
+
+/* e3_conv_pack_weight layouts: 0 plain forward, 1 upsampling forward, 2 backward of the plain
+ * conv, 3 backward of the upsampling conv (pass as the `upsample` argument). */
+#define E3_CONV_PACK_FWD 0
+#define E3_CONV_PACK_UP_FWD 1
+#define E3_CONV_PACK_BWD 2
+#define E3_CONV_PACK_UP_BWD 3
+
+/* Backward of e3_styled_conv3x3_fwd (upsample = 0) / e3_styled_conv3x3_up_fwd (upsample = 1).
+ * dy, y: [B,H',W',cout] NHWC (H' = 2H when upsampling) — upstream gradient and saved output;
+ * x [B,H,W,cin] the saved input; s, d, noise, noise_w, act_bias as in the forward call;
+ * wpacked_bwd from e3_conv_pack_weight(layout 2 or 3).
+ * Outputs: dx [B,H,W,cin]; ds [B,cin] = dL/ds; dd [B,cout] = dL/dd (NULL when the layer does not
+ * demodulate).  Feed ds, dd to e3_modconv_styles_bwd for the latent gradient.
+ * The upsampling variant runs on the tensor cores only (E3_ERR_UNSUPPORTED unless H, W are powers
+ * of two >= 8, cout % 64 == 0, cin % 128 == 0); the plain variant falls back to the CUDA-core
+ * GEMM for cin, cout multiples of 16. */
+size_t e3_styled_conv_bwd_scratch_bytes(int batch, int h, int w, int cin, int cout, int upsample);
+int e3_styled_conv3x3_bwd(const float* dy, const float* y, const float* x, const void* wpacked_bwd,
+                          const float* s, const float* d, const float* noise,
+                          int64_t noise_batch_stride, const float* noise_w, const float* act_bias,
+                          float* dx, float* ds, float* dd, int batch, int h, int w, int cin,
+                          int cout, int upsample, void* scratch, size_t scratch_bytes,
+                          uint32_t flags, void* stream);
+
+/* Backward of e3_torgb_fwd with respect to x and s: drgb [B,3,H,W] NCHW -> dx [B,H,W,cin],
+ * ds [B,cin].  (The skip gradient is drgb itself, or its e3_upfirdn2d adjoint: down = 2,
+ * pad (1,1).) */
+size_t e3_torgb_bwd_scratch_bytes(int batch, int cin);
+int e3_torgb_bwd(const float* drgb, const float* x, const float* weight, const float* s, float* dx,
+                 float* ds, int batch, int h, int w, int cin, void* scratch, size_t scratch_bytes,
+                 void* stream);
+
+/* Adjoint of e3_modconv_styles: dlatent [B,512] from ds [B,cin] and (when demodulating, else
+ * NULL) dd [B,cout]; s, d, wsq as produced / consumed by the forward call. */
+int e3_modconv_styles_bwd(const float* ds, const float* dd, const float* s, const float* d,
+                          const float* wsq, const float* mod_w, int batch, int cin, int cout,
+                          int ksize, float* dlatent, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Image-parallel inversion record: packs, per image, the renderer latent
  * w+ [9*256], the decoder latent [n_latent*512] and K metric scalars into one contiguous
  * fp32 row of the all-gather send buffer, computing the metrics (mean squared error and

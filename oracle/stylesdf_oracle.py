@@ -220,11 +220,18 @@ def sdf_query(sd, points, styles, dist_radius=0.12):
 # --------------------------------------------------------------------------------------
 # StyleGAN2 ops
 # --------------------------------------------------------------------------------------
-def fused_leaky_relu(x, bias=None, negative_slope=0.2, scale=SQRT2):
+def fused_leaky_relu(x, bias=None, negative_slope=0.2, scale=SQRT2, gate=None):
     """fused_bias_act semantics — op/fused_bias_act_kernel.cu:36-47, op/fused_act.py:107-115:
-    y = leaky_relu(x + b[c]) * scale, bias along dim 1."""
+    y = leaky_relu(x + b[c]) * scale, bias along dim 1.
+
+    `gate` (bool tensor, test aid): take the branch decisions x + b > 0 from outside instead of
+    from this evaluation.  Gradient parity tests pass the signs of the CUDA forward here, so that
+    elements sitting on the kink within float32 round-off (where the derivative is ambiguous)
+    do not decide the comparison."""
     if bias is not None:
         x = x + bias.reshape(1, -1, *([1] * (x.ndim - 2)))
+    if gate is not None:
+        return torch.where(gate, x, x * negative_slope) * scale
     return F.leaky_relu(x, negative_slope) * scale
 
 
@@ -294,11 +301,11 @@ def modulated_conv2d(x, style, sd, key, demodulate=True, upsample=False,
     return out.reshape(b, o, out.shape[2], out.shape[3])
 
 
-def styled_conv(x, style, noise, sd, key, upsample=False):
+def styled_conv(x, style, noise, sd, key, upsample=False, gate=None):
     """StyledConv.forward — stylesdf_model.py:494-507 (noise :459-466, act op/fused_act.py)."""
     out = modulated_conv2d(x, style, sd, key + "conv.", upsample=upsample)
     out = out + sd[key + "noise.weight"] * noise
-    return fused_leaky_relu(out, sd[key + "activate.bias"])
+    return fused_leaky_relu(out, sd[key + "activate.bias"], gate=gate)
 
 
 def to_rgb(x, style, skip, sd, key, upsample=True):
@@ -320,23 +327,30 @@ def decoder_num_layers(sd):
     return n
 
 
-def decoder_forward(sd, features, latent, noises=None):
+def decoder_forward(sd, features, latent, noises=None, gates=None, acts=None):
     """Decoder.forward with input_is_latent=True, randomize_noise=False —
     stylesdf_model.py:742-797 (latent indexing :764-792; noise buffers :652-656,707-710).
 
     features [B,256,R,R]; latent [B,n_latent,512] -> image [B,3,size,size]
+    gates (test aid): per StyledConv layer the branch decisions of its leaky-ReLU (see
+    fused_leaky_relu); acts: a list that receives the StyledConv outputs in order.
     """
     n_layers = decoder_num_layers(sd)
     if noises is None:
         noises = [sd[f"decoder.noises.noise_{i}"] for i in range(n_layers)]
-    out = styled_conv(features, latent[:, 0], noises[0], sd, "decoder.conv1.")
+    g = (lambda k: gates[k]) if gates is not None else (lambda k: None)
+    keep = acts.append if acts is not None else (lambda t: None)
+    out = styled_conv(features, latent[:, 0], noises[0], sd, "decoder.conv1.", gate=g(0))
+    keep(out)
     skip = to_rgb(out, latent[:, 1], None, sd, "decoder.to_rgb1.", upsample=False)
     i = 1
     for stage in range((n_layers - 1) // 2):
         out = styled_conv(out, latent[:, i], noises[2 * stage + 1], sd,
-                          f"decoder.convs.{2 * stage}.", upsample=True)
+                          f"decoder.convs.{2 * stage}.", upsample=True, gate=g(2 * stage + 1))
+        keep(out)
         out = styled_conv(out, latent[:, i + 1], noises[2 * stage + 2], sd,
-                          f"decoder.convs.{2 * stage + 1}.")
+                          f"decoder.convs.{2 * stage + 1}.", gate=g(2 * stage + 2))
+        keep(out)
         skip = to_rgb(out, latent[:, i + 2], skip, sd, f"decoder.to_rgbs.{stage}.")
         i += 2
     return skip
