@@ -137,19 +137,28 @@ __device__ __forceinline__ float sin_fast_accurate(float a) {
   return __int_as_float(__float_as_int(res) ^ (__float_as_int(jm) << 31));
 }
 
-// sin(x) = sin.approx (MUFU) of x reduced EXACTLY to [-pi, pi] by a 3-term Cody-Waite split of 2*pi.
-// On [-pi, pi] the hardware approximation has max abs error 2^-21.41 (3.6e-7, CUDA math API) and the
-// reduction keeps |x| up to ~1e3 inside that range without losing phase accuracy (the raw __sinf
-// range reduction would add |x| * 6e-8).  ~7 instructions, the transcendental on the otherwise idle
-// MUFU pipe.  Used by the tensor-core renderer, whose operands are quantised to hi+lo bf16 (2^-17
-// relative, 20x coarser than this error); the exact-fp32 renderer keeps the polynomial version.
-__device__ __forceinline__ float sin_mufu_reduced(float a) {
+// sin(x) = sin.approx (MUFU) of x reduced to [-pi, pi] by a 2-term Cody-Waite split of 2*pi:
+// 6.28125 has 9 significant bits, so j*6.28125 and x - j*6.28125 are exact for |x| < 2^12; the second
+// term carries the remainder of 2*pi rounded to fp32 (representation error 6e-11 * j).  On [-pi, pi]
+// the hardware approximation has max abs error 2^-21.41 (3.6e-7, CUDA math API); the raw __sinf range
+// reduction would add |x| * 6e-8.  6 instructions (FFMA, FADD, 2 FFMA, FMUL.RZ, MUFU.SIN), the
+// transcendental on the otherwise idle MUFU pipe.  Used by the tensor-core renderer, whose operands
+// are quantised to hi+lo bf16 (2^-17 relative, 20x coarser than this error); the exact-fp32 renderer
+// keeps the polynomial version.
+__device__ __forceinline__ float reduce_2pi(float a) {
   const float jm = fmaf(a, 0.159154943f, 12582912.0f);  // rint(a / 2pi) + 1.5 * 2^23
   const float j = jm - 12582912.0f;
-  float r = fmaf(j, -6.28125f, a);
-  r = fmaf(j, -1.93500518798828125e-3f, r);
-  r = fmaf(j, -3.019915981956752e-7f, r);
-  return __sinf(r);
+  const float r = fmaf(j, -6.28125f, a);
+  return fmaf(j, -1.9353071795864769e-3f, r);
+}
+__device__ __forceinline__ float sin_mufu_reduced(float a) { return __sinf(reduce_2pi(a)); }
+
+// x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi), for a pair, packed as the UMMA operands want
+// them (element 0 in the low half): 2 F2FP + 2 bit extractions + 2 FADD per pair.
+__device__ __forceinline__ void split_pair_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - h1), "f"(v0 - h0));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -69,26 +69,13 @@ __device__ __forceinline__ uint32_t a_chunk_off(int m, int c16) {
 __device__ __forceinline__ void store_a8(SmemBwd& sm, int m, int n0, const float* v) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+  for (int i = 0; i < 4; ++i) split_pair_bf16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
   const uint32_t off = (uint32_t)(n0 >> 6) * A_KBLOCK_BYTES + a_chunk_off(m, (n0 & 63) >> 3);
   *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// exact reduction to [-pi, pi] (3-term split of 2*pi, as sin_mufu_reduced), then MUFU sin / cos
-__device__ __forceinline__ float reduce_2pi(float a) {
-  const float jm = fmaf(a, 0.159154943f, 12582912.0f);
-  const float j = jm - 12582912.0f;
-  float r = fmaf(j, -6.28125f, a);
-  r = fmaf(j, -1.93500518798828125e-3f, r);
-  return fmaf(j, -3.019915981956752e-7f, r);
-}
+// exact reduction to [-pi, pi] (reduce_2pi, common.cuh), then MUFU sin / cos
 __device__ __forceinline__ float cos_reduced(float a) { return __cosf(reduce_2pi(a)); }
 __device__ __forceinline__ void sincos_reduced(float a, float& s, float& c) {
   const float r = reduce_2pi(a);

@@ -49,6 +49,7 @@ constexpr int A_BYTES = 4 * A_KBLOCK_BYTES;    // one of hi / lo: 64 KB
 // timing experiments only (profiles/whatif_render.py): results are numerically WRONG with these set
 constexpr uint32_t DBG_SKIP_LO_MMA = 1u << 30;  // issue only the hi*hi products (1/3 of the MMAs)
 constexpr uint32_t DBG_NO_SIN = 1u << 31;       // epilogue without the sin evaluation
+constexpr uint32_t DBG_NO_WSTREAM = 1u << 29;   // no weight TMA, MMAs read whatever the ring holds
 
 struct SmemTC {
   uint8_t a_hi[A_BYTES];  // also the fp32 [256][128] composite buffer together with a_lo
@@ -81,13 +82,7 @@ __device__ __forceinline__ uint32_t a_chunk_off(int m, int c16) {
 __device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float* v) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+  for (int i = 0; i < 4; ++i) split_pair_bf16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
   const uint32_t off = (uint32_t)(n0 >> 6) * A_KBLOCK_BYTES + a_chunk_off(m, (n0 & 63) >> 3);
   *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -101,7 +96,11 @@ __device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float*
 // which is what bounds the kernel at CL = 1 (profiles/r01e_whatif_render.txt).
 // wmap: 2-D tensor map over the pre-swizzled weight stream viewed as rows of 64 bf16 (128 B), box =
 // one 128-row tile, no hardware swizzle; use_wmap selects cp.async.bulk.tensor over the 1-D bulk copy.
-template <int MODE, int CL>
+// STASH: training build that also writes the pre-sin phases for e3_render_bwd (a compile-time switch:
+// even predicated off, the per-element address arithmetic would cost the inference build ~3
+// instruction slots per element).
+template <int MODE, int CL, bool STASH>
+// 18 warps: one scheduler holds 5 of them, so 16384 / (5 * 32) = 102 -> 96 registers per thread
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ CUtensorMap wmap,
                        const int use_wmap) {
@@ -136,7 +135,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer: 16 weight tiles per layer, in consumption order =====
-    if (lane == 0) {
+    if (lane == 0 && !(a.p.flags & DBG_NO_WSTREAM)) {
       const uint8_t* stream = reinterpret_cast<const uint8_t*>(a.packed + OFF_TC_STREAM);
       const int per_tile = gemm_layers * TC_TILES_PER_LAYER;
       uint32_t stage = 0, phase = 0;
@@ -168,6 +167,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       const uint32_t idesc = tc::make_idesc_bf16_f32(128, 256);
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
       const bool skip_lo = (a.p.flags & DBG_SKIP_LO_MMA) != 0;
+      const bool no_w = (a.p.flags & DBG_NO_WSTREAM) != 0;
       uint32_t stage = 0, phase = 0, pa = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         const bool tr = a.trace && blockIdx.x == 0 && t == 1;
@@ -185,8 +185,10 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             // 256 output columns instead of twice (shared-memory bandwidth bounds this kernel).
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) {  // pr 0: W_hi block, pr 1: W_lo block
-              mbar_wait(&sm.full[stage], phase);
-              mbar_wait(&sm.full[stage + 1], phase);
+              if (!no_w) {
+                mbar_wait(&sm.full[stage], phase);
+                mbar_wait(&sm.full[stage + 1], phase);
+              }
               tc::fence_after_thread_sync();
               const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
 #pragma unroll
@@ -201,6 +203,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               }
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
+                if (no_w) continue;
                 if (CL == 1) tc::mma_commit(&sm.empty[stage + h]);
                 else tc::mma_commit_multicast(&sm.empty[stage + h], cl_mask);
               }
@@ -340,7 +343,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       };
       const bool taps = (MODE == 0) && a.out.feats_taps && valid;
       // training: pre-sin phases of every FiLM layer for e3_render_bwd ([layer][channel][row])
-      float* stash = (a.stash && !dummy) ? a.stash + (size_t)tile * STASH_FLOATS_PER_TILE + m : nullptr;
+      float* stash = (STASH && !dummy) ? a.stash + (size_t)tile * STASH_FLOATS_PER_TILE + m : nullptr;
       const bool tr = a.trace && blockIdx.x == 0 && slot == 1 && tid == 64;
       if (tr) a.trace[0] = clock64();
 
@@ -362,7 +365,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float arg = fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]);
-              if (stash) stash[(size_t)(n + i) * TCM] = arg;
+              if (STASH && stash) stash[(size_t)(n + i) * TCM] = arg;
               v[i4 * 4 + i] = sin_mufu_reduced(arg);
             }
           }
@@ -400,7 +403,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
-              if (stash) stash[(size_t)(l * SW + n0 + i) * TCM] = arg;
+              if (STASH && stash) stash[(size_t)(l * SW + n0 + i) * TCM] = arg;
               v[i] = no_sin ? arg * 1e-3f : sin_mufu_reduced(arg);
             }
             if (last) {
@@ -517,7 +520,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               pre = fmaf(e1[i], v1, pre);
               pre = fmaf(e2[i], v2, pre);
               const float arg8 = fmaf(sm.film[8][0][n + i], pre, sm.film[8][1][n + i]);
-              if (stash) stash[(size_t)(8 * SW + n + i) * TCM] = arg8;
+              if (STASH && stash) stash[(size_t)(8 * SW + n + i) * TCM] = arg8;
               const float f = sin_mufu_reduced(arg8);
               c0 = fmaf(q0[i], f, c0);
               c1 = fmaf(q1[i], f, c1);
@@ -597,11 +600,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int MODE, int CL>
+template <int MODE, int CL, bool STASH = false>
 static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
   static thread_local bool attr_set = false;
   const int smem_bytes = (int)sizeof(SmemTC) + 1024;
-  auto* fn = siren_render_tc_kernel<MODE, CL>;
+  auto* fn = siren_render_tc_kernel<MODE, CL, STASH>;
   if (!attr_set) {
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
@@ -662,6 +665,7 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   if (const char* tp = getenv("E3DGE_RENDER_TRACE_PTR"))  // measurement aid, see RenderArgs::trace
     a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
   const int cl = render_cluster_size();
+  if (a.stash) return mode == 0 ? launch_tc_variant<0, 1, true>(a, stream) : launch_tc_variant<1, 1, true>(a, stream);
   if (mode == 0) {
     if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
     if (cl == 2) return launch_tc_variant<0, 2>(a, stream);

@@ -67,6 +67,11 @@ def main():
         loss = (state["rout"]["features"] ** 2).mean() + (state["rout"]["gen_thumb_imgs"] ** 2).mean()
         torch.autograd.grad(loss, [state["rw"]])
 
+    if len(sys.argv) > 2 and sys.argv[2] == "train_only":  # profiler runs: a few training steps only
+        for _ in range(3):
+            fwd_bwd()
+        torch.cuda.synchronize()
+        return
     t = {"generator fwd (inference)": timed(fwd_infer), "generator fwd (training, stash)": timed(fwd_train),
          "generator fwd+bwd": timed(fwd_bwd), "renderer fwd (training, stash)": timed(render_train),
          "renderer fwd+bwd": timed(render_fwd_bwd)}
