@@ -203,6 +203,7 @@ def run_ours(args):
 
     if rank == 0:
         line.update(kernel_roofline(G, resident, dev, flush, args))
+        line["train_step"] = train_step_timing(G, resident, flush, args)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sd, make_inputs(0), steps=2)
         print(json.dumps(line), flush=True)
@@ -281,6 +282,39 @@ def kernel_roofline(G, inp, dev, flush, args):
                          "achieved": tf32_equiv, "peak": ffma_peak, "unit": "TFLOP/s",
                          "frac": tf32_equiv / ffma_peak,
                          "peak_source": "measured here (register-only FFMA probe)"}}}
+
+
+def train_step_timing(G, inp, flush, args):
+    """Secondary figure (not the headline metric): the same batch through the generator with the
+    backward kernels — forward writing the stash, then dL/d(w+), dL/d(decoder latent) of an image
+    loss (frozen generator, as the E3DGE encoder training uses it: BASELINE.json configs[3])."""
+    for p in G.parameters():
+        p.requires_grad_(False)
+    n = max(3, min(args.steps, 10))
+
+    def one():
+        w = inp["w"].clone().requires_grad_(True)
+        wd = inp["w_dec"].clone().requires_grad_(True)
+        out = G([w, wd], inp["cam_poses"], inp["focal"], inp["near"], inp["far"], input_is_latent=True,
+                randomize_noise=True)
+        loss = (out["gen_imgs"] ** 2).mean() + (out["gen_thumb_imgs"] ** 2).mean()
+        torch.autograd.grad(loss, [w, wd])
+
+    for _ in range(3):
+        one()
+    times = []
+    for _ in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        one()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = statistics.median(times)
+    return {"what": "generator forward (with stash) + backward to the latents, batch 8, 1 GPU",
+            "ms_per_step": ms, "frames_per_s": BATCH / (ms / 1e3)}
 
 
 def best_cpu_threads(sd, inp):
