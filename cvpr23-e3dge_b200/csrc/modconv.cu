@@ -136,7 +136,18 @@ __global__ void __launch_bounds__(256, 2) conv_gemm_ffma_kernel(const __grid_con
       xx += tap % 3 - 1;
     }
     ra[0] = ra[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a_row_ok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+    if (TAPS == 9 && a.planar) {
+      // up-conv backward: x is the fp32 parity-planar gradient [py][px][B][H+1][W+1][Cin], already
+      // multiplied by the demodulation; tap (ky,kx) reads plane (ky&1, kx&1) at (y + (ky>>1), x + (kx>>1))
+      if (a_row_ok) {
+        const int ky = tap / 3, kx = tap % 3;
+        const int plane = (ky & 1) * 2 + (kx & 1);
+        const float4* src = reinterpret_cast<const float4*>(
+            a.x + ((((size_t)plane * a.B + ab) * (a.H + 1) + ay + (ky >> 1)) * (a.W + 1) + ax + (kx >> 1)) * a.Cin + ci0);
+        ra[0] = src[0];
+        ra[1] = src[1];
+      }
+    } else if (a_row_ok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
       const float4* src =
           reinterpret_cast<const float4*>(a.x + (((size_t)ab * a.H + yy) * a.W + xx) * a.Cin + ci0);
       const float4* sp = reinterpret_cast<const float4*>(a.s + (size_t)ab * a.Cin + ci0);
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(256) pack_record_kernel(const float* __restric
 }
 
 int conv_gemm_ffma_launch(const ConvGemmArgs& a, int taps, cudaStream_t stream) {
-  E3_REQUIRE(a.Cin % CG_BK == 0 && a.N % 4 == 0 && !a.planar, E3_ERR_UNSUPPORTED,
+  E3_REQUIRE(a.Cin % CG_BK == 0 && a.N % 4 == 0 && (!a.planar || taps == 9), E3_ERR_UNSUPPORTED,
              "CUDA-core conv: needs Cin %% 16 == 0 and N %% 4 == 0 (got Cin=%d N=%d)", a.Cin, a.N);
   const int64_t M = (int64_t)a.B * a.H * a.W;
   dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (a.N + CG_BN - 1) / CG_BN);

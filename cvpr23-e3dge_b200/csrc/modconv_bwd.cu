@@ -142,6 +142,9 @@ __global__ void chunk_sum_kernel(const float* __restrict__ partial, float* __res
 // (stylesdf_model.py:283-291, 331-346), times the demodulation, written parity-planar and split:
 //   dT[b,t,u,o] = d[b,o] * sum_{i,j} da[b, t-i+1, u-j+1, o] * kb[i]*kb[j],  t,u in [0, 2H]
 //   planar index [(t&1)*2 + (u&1)][b][t>>1][u>>1][o]; entries with t > 2H or u > 2W are zero.
+// SPLIT: bf16 hi / lo halves for the tensor-core GEMM; otherwise one fp32 image (`hi` reinterpreted)
+// for the CUDA-core GEMM.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) upconv_dT_kernel(const float* __restrict__ da, const float* __restrict__ d,
                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                         int B, int H, int W, int cout) {
@@ -178,12 +181,20 @@ __global__ void __launch_bounds__(256) upconv_dT_kernel(const float* __restrict_
         }
       }
     }
-    __align__(16) __nv_bfloat16 h8[8], l8[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tc::split_bf16(acc[i] * d[(size_t)b * cout + c + i], h8[i], l8[i]);
     const size_t o = ((((size_t)plane * B + b) * (H + 1) + k) * (W + 1) + l) * cout + c;
-    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h8);
-    *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= d[(size_t)b * cout + c + i];
+    if (SPLIT) {
+      __align__(16) __nv_bfloat16 h8[8], l8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc::split_bf16(acc[i], h8[i], l8[i]);
+      *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h8);
+      *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l8);
+    } else {
+      float* out32 = reinterpret_cast<float*>(hi) + o;
+      *reinterpret_cast<float4*>(out32) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(out32 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
   }
 }
 
@@ -334,16 +345,21 @@ extern "C" int e3_styled_conv3x3_bwd(const float* dy, const float* y, const floa
       return rc;
     }
   } else {
-    E3_REQUIRE(tcore, E3_ERR_UNSUPPORTED,
-               "e3_styled_conv3x3_bwd: up-conv shape B=%d H=%d W=%d cin=%d cout=%d is outside the tensor-core path "
-               "(power-of-two H, W >= 8, cout %% 64 == 0, cin %% 128 == 0)", batch, h, w, cin, cout);
+    // the planar image holds 2 bf16 halves or 1 fp32 copy: the same bytes either way
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(split);
     __nv_bfloat16* lo = hi + tc_conv_planar_elems(batch, h, w, cout);
     const int64_t total = (int64_t)tc_conv_planar_elems(batch, h, w, cout) / 8;
-    upconv_dT_kernel<<<grid_cap((total + 255) / 256), 256, 0, st>>>(da, d, hi, lo, batch, h, w, cout);
-    E3_CUDA(cudaGetLastError());
     a.planar = 1;
-    if ((rc = tc_conv_launch_presplit(a, 9, wbf16, hi, lo, st))) return rc;
+    if (tcore) {
+      upconv_dT_kernel<true><<<grid_cap((total + 255) / 256), 256, 0, st>>>(da, d, hi, lo, batch, h, w, cout);
+      E3_CUDA(cudaGetLastError());
+      if ((rc = tc_conv_launch_presplit(a, 9, wbf16, hi, lo, st))) return rc;
+    } else {
+      upconv_dT_kernel<false><<<grid_cap((total + 255) / 256), 256, 0, st>>>(da, d, hi, lo, batch, h, w, cout);
+      E3_CUDA(cudaGetLastError());
+      a.x = reinterpret_cast<const float*>(split);
+      if ((rc = conv_gemm_ffma_launch(a, 9, st))) return rc;
+    }
   }
 
   // 3. dx = dxs * s (in place), ds = sum_p dxs * x

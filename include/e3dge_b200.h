@@ -327,9 +327,8 @@ int e3_torgb_fwd(const float* x, const float* weight, const float* s, const floa
  * wpacked_bwd from e3_conv_pack_weight(layout 2 or 3).
  * Outputs: dx [B,H,W,cin]; ds [B,cin] = dL/ds; dd [B,cout] = dL/dd (NULL when the layer does not
  * demodulate).  Feed ds, dd to e3_modconv_styles_bwd for the latent gradient.
- * The upsampling variant runs on the tensor cores only (E3_ERR_UNSUPPORTED unless H, W are powers
- * of two >= 8, cout % 64 == 0, cin % 128 == 0); the plain variant falls back to the CUDA-core
- * GEMM for cin, cout multiples of 16. */
+ * Tensor cores when H, W are powers of two >= 8, cout % 64 == 0 and cin % 128 == 0 (flags as in
+ * the forward call), else the exact-fp32 CUDA-core GEMM; cin, cout must be multiples of 16. */
 size_t e3_styled_conv_bwd_scratch_bytes(int batch, int h, int w, int cin, int cout, int upsample);
 int e3_styled_conv3x3_bwd(const float* dy, const float* y, const float* x, const void* wpacked_bwd,
                           const float* s, const float* d, const float* noise,

@@ -237,7 +237,9 @@ def _module_sd(mod, prefix):
 
 @pytest.mark.parametrize("cin,cout,hw,batch,up,backend", [
     (64, 128, 8, 3, False, "auto"), (128, 128, 16, 2, True, "auto"), (256, 128, 8, 5, True, "auto"),
-    (16, 32, 10, 2, False, "auto"), (64, 128, 8, 2, False, "fp32")])
+    (16, 32, 10, 2, False, "auto"), (64, 128, 8, 2, False, "fp32"),
+    (32, 16, 6, 2, True, "auto"), (128, 128, 8, 2, True, "fp32"),      # up-conv backward on the CUDA cores
+    (64, 32, 32, 1, True, "auto")])                                    # the 64 -> 32 tail of a size-1024 decoder
 def test_styled_conv_backward_vs_oracle_autograd(cin, cout, hw, batch, up, backend):
     from e3dge_b200.stylesdf_model import StyledConv
     torch.manual_seed(5)
