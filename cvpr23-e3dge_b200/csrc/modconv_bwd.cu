@@ -240,14 +240,17 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict_
 
 // dlatent[b,:] = ( ds[b,:] - s[b,:] * scale^2 * sum_o dd[b,o] d[b,o]^3 wsq[o,:] ) . mod_w / sqrt(512)
 // (adjoint of mod_style_kernel + demod_kernel, modconv.cu; stylesdf_model.py:319-326)
+// grid (8, B): every block rebuilds the cin-vector (cheap, keeps one launch) and produces 64 of the
+// 512 latent entries, 4 partial sums per entry.
 __global__ void __launch_bounds__(256) styles_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ dd,
                                                          const float* __restrict__ s, const float* __restrict__ d,
                                                          const float* __restrict__ wsq, const float* __restrict__ mod_w,
                                                          int cin, int cout, float scale2, float* __restrict__ dlatent) {
-  extern __shared__ float sm[];  // e[cout] | dst[cin]
+  extern __shared__ float sm[];  // e[cout] | dst[cin] | part[4][64]
   float* e = sm;
   float* dst = sm + cout;
-  const int b = blockIdx.x;
+  float* part = dst + cin;
+  const int b = blockIdx.y, k0 = blockIdx.x * 64;
   if (dd) {
     for (int o = threadIdx.x; o < cout; o += blockDim.x) {
       const float dv = d[(size_t)b * cout + o];
@@ -258,18 +261,36 @@ __global__ void __launch_bounds__(256) styles_bwd_kernel(const float* __restrict
   for (int i = threadIdx.x; i < cin; i += blockDim.x) {
     float v = ds[(size_t)b * cin + i];
     if (dd) {
-      float acc = 0.f;
-      for (int o = 0; o < cout; ++o) acc = fmaf(e[o], wsq[(size_t)o * cin + i], acc);
-      v -= s[(size_t)b * cin + i] * scale2 * acc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* wp = wsq + i;
+      int o = 0;
+#pragma unroll 2
+      for (; o + 4 <= cout; o += 4) {
+        a0 = fmaf(e[o], wp[(size_t)o * cin], a0);
+        a1 = fmaf(e[o + 1], wp[(size_t)(o + 1) * cin], a1);
+        a2 = fmaf(e[o + 2], wp[(size_t)(o + 2) * cin], a2);
+        a3 = fmaf(e[o + 3], wp[(size_t)(o + 3) * cin], a3);
+      }
+      for (; o < cout; ++o) a0 = fmaf(e[o], wp[(size_t)o * cin], a0);
+      v -= s[(size_t)b * cin + i] * scale2 * ((a0 + a1) + (a2 + a3));
     }
     dst[i] = v;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 512; k += blockDim.x) {
-    float acc = 0.f;
-    for (int i = 0; i < cin; ++i) acc = fmaf(dst[i], mod_w[(size_t)i * 512 + k], acc);
-    dlatent[(size_t)b * 512 + k] = acc * 0.04419417382415922f;
+  const int kk = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 4 groups split the cin range
+  const int per = (cin + 3) / 4, i0 = grp * per, i1 = min(cin, i0 + per);
+  float a0 = 0.f, a1 = 0.f;
+  int i = i0;
+  for (; i + 2 <= i1; i += 2) {
+    a0 = fmaf(dst[i], mod_w[(size_t)i * 512 + k0 + kk], a0);
+    a1 = fmaf(dst[i + 1], mod_w[(size_t)(i + 1) * 512 + k0 + kk], a1);
   }
+  if (i < i1) a0 = fmaf(dst[i], mod_w[(size_t)i * 512 + k0 + kk], a0);
+  part[grp * 64 + kk] = a0 + a1;
+  __syncthreads();
+  if (grp == 0)
+    dlatent[(size_t)b * 512 + k0 + kk] =
+        ((part[kk] + part[64 + kk]) + (part[128 + kk] + part[192 + kk])) * 0.04419417382415922f;
 }
 
 int grid_cap(int64_t blocks) {
@@ -402,7 +423,7 @@ extern "C" int e3_modconv_styles_bwd(const float* ds, const float* dd, const flo
   E3_REQUIRE(!dd || (s && d && wsq && cout > 0), E3_ERR_BAD_ARG,
              "e3_modconv_styles_bwd: the demodulation term needs s, d, wsq and cout");
   const float scale2 = 1.f / (float)(cin * ksize * ksize);
-  styles_bwd_kernel<<<batch, 256, (size_t)(cin + cout) * sizeof(float), as_stream(stream)>>>(
+  styles_bwd_kernel<<<dim3(8, batch), 256, (size_t)(cin + cout + 256) * sizeof(float), as_stream(stream)>>>(
       ds, dd, s, d, wsq, mod_w, cin, cout, scale2, dlatent);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
