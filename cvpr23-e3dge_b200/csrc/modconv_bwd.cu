@@ -1,7 +1,7 @@
 // Backward of the modulated-conv decoder (channels-last fp32 activations), sm_100a.
 //
 // What autograd gives the reference through Decoder.forward (stylesdf_model.py:742-797) when the
-// E3DGE runners back-propagate image losses into the encoders (trainer.py:881-900): gradients with
+// E3DGE runners back-propagate image losses into the encoders (trainer.py:881-900, generator frozen at :1569): gradients with
 // respect to the layer input (-> the renderer's feature map) and the per-layer latent
 // (ModulatedConv2d.modulation, stylesdf_model.py:319).  The generator weights are frozen on this
 // path: no weight, noise-strength or bias gradients.

@@ -85,7 +85,7 @@ int launch_render_tc(const RenderArgs& a, int mode, cudaStream_t stream);
 // ---- backward (render_siren_bwd_tc.cu) ---------------------------------------------------------
 // Gradients of the fused renderer with respect to its differentiable inputs: the FiLM table (hence
 // the w / w+ latents), the local texture modulation and the sample positions.  The generator's own
-// weights are frozen on the E3DGE path (trainer.py:1391-1399 trains encoders only), so no weight
+// weights are frozen on the E3DGE path (trainer.py:1569 freezes the generator, the encoders train), so no weight
 // gradients are produced.
 constexpr int BWD_STAT_FLOATS = 9 * 2 * SW;  // per (CTA, image): [layer][sum gpre, sum gpre*arg][256]
 struct RenderBwdArgs {

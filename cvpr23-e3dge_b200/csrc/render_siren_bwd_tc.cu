@@ -3,7 +3,7 @@
 // What the reference gets from autograd through VolumeFeatureRenderer.forward
 // (volume_renderer.py:1865-1972 -> render_rays :1183-1298 -> run_network :1052-1128 ->
 // SirenGenerator.forward :240-264 -> volume_integration :809-943) when the E3DGE runners train
-// their encoders against the frozen generator (trainer.py:881-900, e3dge_full_runner.py:219-306):
+// their encoders against the frozen generator (trainer.py:881-900, generator frozen at :1569, e3dge_full_runner.py:219-306):
 // gradients with respect to the FiLM frequencies / phases (hence the w / w+ latents), the local
 // texture modulation (alpha, beta) of the PIFu branch and the sample positions (eikonal term,
 // volume_renderer.py:796-802).  One persistent kernel per call, mirror image of

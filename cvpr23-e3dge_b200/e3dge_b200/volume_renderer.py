@@ -10,7 +10,7 @@ Not provided (SURVEY.md §8 out of scope / "next" rows): marching-cubes mesh ext
 (alpha, beta) texture modulation), second-order gradients (the eikonal terms are returned
 as values of the backward kernel, without a graph of their own).
 
-Training (encoders against the frozen generator, trainer.py:881-900): `_FilmFn`, `_RenderFn`
+Training (encoders against the frozen generator, trainer.py:881-900, generator frozen at :1569): `_FilmFn`, `_RenderFn`
 and `_PointsFn` bind e3_film_bwd / e3_render_bwd / e3_siren_points_bwd, so gradients reach the
 w / w+ latents, the local texture modulation and explicit query points.  The generator's own
 parameters and the cameras receive no gradient.

@@ -162,7 +162,7 @@ int e3_siren_points_fwd_train(const void* packed, const float* film, const float
 /* ------------------------------------------------------------------------------------
  * Backward of the renderer — what autograd gives the reference through
  * VolumeFeatureRenderer.forward when the E3DGE runners train encoders against the frozen
- * generator (trainer.py:881-900; e3dge_full_runner.py:219-306): gradients with respect to the
+ * generator (trainer.py:881-900, generator frozen at :1569; e3dge_full_runner.py:219-306): gradients with respect to the
  * FiLM table (-> w / w+ through e3_film_bwd), the local texture modulation and the sample
  * positions (volume_renderer.py:796-802, get_eikonal_term).  The generator weights are
  * frozen on this path: no weight gradients.  Camera parameters receive no gradient.
@@ -310,7 +310,7 @@ int e3_torgb_fwd(const float* x, const float* weight, const float* s, const floa
 /* ------------------------------------------------------------------------------------
  * Decoder backward — what autograd gives the reference through Decoder.forward
  * (stylesdf_model.py:742-797) when image losses are back-propagated into the encoders
- * (trainer.py:881-900): gradients with respect to the layer input and the layer's latent.
+ * (trainer.py:881-900, generator frozen at :1569): gradients with respect to the layer input and the layer's latent.
  * The generator weights are frozen on this path: no weight / bias / noise-strength gradients.
  * ---------------------------------------------------------------------------------- */
 
