@@ -27,6 +27,7 @@ def rendering_options(**over):
             no_sdf=False, add_fg_mask=False, enable_local_model=False, return_feats=False,
             return_feats_layers=[1, 3, 5, 7], local_modulation_layer=False,
             local_modulation_layer_in_backbone=False, use_integrated_surface_normal=False,
+            L_pred_tex_modulations=False, L_pred_geo_modulations=False,
             sample_near_surface=False, sample_uniform_grid=False, uniform_grid_sampling_num=2048,
             surface_sampling_stdv=0.01,
             camera=Opt(dist_radius=0.12, fov=6, azim=0.3, elev=0.15, uniform=False))

@@ -658,6 +658,15 @@ class VolumeFeatureRenderer(nn.Module):
         self.local_batch = local_data_batch if self.enable_local_model else None
         if local_data_batch is not None and "tex_modulation" in local_data_batch:
             kwargs.setdefault("local_tex_modulation", local_data_batch["tex_modulation"])
+        elif (local_data_batch is not None and "feats" in local_data_batch and not sample_mode
+              and getattr(self.network, "netLocal", None) is not None):
+            # SirenLocalGlobal.forward_backbone (volume_renderer.py:323-336): the caller's netLocal maps
+            # the per-sample local features [B,H,W,S,301] to the texture modulation (alpha | beta)
+            if getattr(self.opt, "L_pred_geo_modulations", False):
+                raise NotImplementedError("geometry modulation of the local branch (volume_renderer.py:338-345) "
+                                          "is not built; the shipped scripts use texture modulation only")
+            mods = self.network.netLocal.local_feat_to_tex_modulations_linear(local_data_batch["feats"])
+            kwargs.setdefault("local_tex_modulation", tuple(torch.split(mods, 256, dim=-1)))
         out = self.render(focal, c2w=cam_poses, near=near, far=far, styles=styles,
                           return_eikonal=return_eikonal,
                           return_surface_eikonal=return_surface_eikonal, return_mesh=return_mesh,
@@ -751,12 +760,105 @@ class VolumeFeatureRenderer(nn.Module):
         sdf = self.sdf_query(pts.reshape(B, -1, 3), styles).reshape(z.shape)
         return sdf, pts.detach().norm(dim=-1) - ((fr - nr) / 4)
 
+    # ------------------------------------------------------------------ visibility queries (a17)
+    def _weights_from_sdf(self, sdf, z_vals, rays_d_norm, no_force_stop=True):
+        """The density half of volume_integration (volume_renderer.py:822-886) for sdf [...,S,1],
+        z_vals [...,S], rays_d_norm [...,1]: (visibility, weights), both [...,S,1]."""
+        dists = z_vals[..., 1:] - z_vals[..., :-1]
+        tail = dists[..., 0:1] if no_force_stop else self.inf.expand(dists[..., 0:1].shape)
+        dists = torch.cat([dists, tail], -1) * rays_d_norm
+        if self.with_sdf:
+            alpha = 1 - torch.exp(-self.sdf_activation(-sdf) * dists.unsqueeze(-1))
+        else:
+            alpha = 1 - torch.exp(-F.softplus(sdf) * dists.unsqueeze(-1))
+        vis = torch.cumprod(torch.cat([torch.ones_like(alpha[..., :1, :]), 1. - alpha + 1e-10], -2), -2)
+        vis = vis[..., :-1, :]
+        w = alpha * vis
+        if self.force_background and not no_force_stop:
+            w = torch.cat([w[..., :-1, :], 1 - w[..., :-1, :].sum(-2, keepdim=True)], -2)
+        return vis, w
+
+    def _reference_view_rays(self, wd_space_pts, ref_img_info):
+        """Shared head of the two visibility queries (volume_renderer.py:1340-1376, 1512-1545): the ray
+        from the reference camera through every query point.  Returns points [B,N,S,1,3], the ray
+        origin [B,1,1,1,3], world-space directions [B,N,S,1,3] (unit depth along -z of the reference
+        camera) and the points in the reference camera frame [B,N,S,3]."""
+        B, H, W, S = wd_space_pts.shape[:4]
+        poses = ref_img_info["cam_settings"]["poses"][:, :3, :4].float()
+        extr = ref_img_info["cam_settings"]["extrinsics"][:, :3, :4].float()
+        pts = wd_space_pts.reshape(B, H * W, S, 3).float()
+        ref = torch.einsum("bij,bnsj->bnsi", extr[:, :, :3], pts) + extr[:, None, None, :, 3]
+        d_ref = ref / (-ref[..., 2:3])
+        d_wd = torch.einsum("bij,bnsj->bnsi", poses[:, :, :3], d_ref)
+        rays_o = poses[:, :, 3].reshape(B, 1, 1, 1, 3)
+        return pts.unsqueeze(-2), rays_o, d_wd.unsqueeze(-2), d_ref, ref
+
+    def _march_reference_rays(self, ray_pts, z_vals, viewdirs, styles):
+        """sdf along the query rays -> (visibility, weights) [B,N,S,T,1] with the no_force_stop composite
+        (volume_renderer.py:1428-1470).  Only the density is needed, so the sdf-only kernel runs (the
+        reference evaluates the full network and discards rgb / features)."""
+        B, N, S, T = ray_pts.shape[:4]
+        vis = torch.empty(B, N, S, T, 1, device=ray_pts.device)
+        w = torch.empty_like(vis)
+        step = 64 ** 2
+        for lo in range(0, N, step):
+            chunk = ray_pts[:, lo:lo + step]
+            sdf = self.sdf_query(chunk.reshape(B, -1, 3), styles).reshape(*chunk.shape[:4], 1)
+            ones = torch.ones_like(z_vals[:, lo:lo + step, :, :1])  # normalised view dirs: |d| = 1
+            vis[:, lo:lo + step], w[:, lo:lo + step] = self._weights_from_sdf(sdf, z_vals[:, lo:lo + step], ones)
+        return vis, w
+
+    @torch.no_grad()
+    def query_hitting_probability_fixed_interval(self, wd_space_pts, ref_img_info, return_type="weights"):
+        """Hit probability / visibility of world-space points [B,H,W,S,3] seen from a reference view:
+        re-march the reference camera's ray through every point with the renderer's own depth samples
+        and interpolate at the point's depth — volume_renderer.py:1326-1493."""
+        assert return_type in ("weights", "visibility")
+        assert wd_space_pts.ndim == 5
+        B, H, W, S = wd_space_pts.shape[:4]
+        styles = ref_img_info["pred_latents"][0]
+        out = ref_img_info["global_render_out"]
+        near = out["near"].reshape(B, H * W, 1, 1, 1).float()
+        far = out["far"].reshape(B, H * W, 1, 1, 1).float()
+        pts, rays_o, d_wd, d_ref, _ = self._reference_view_rays(wd_space_pts, ref_img_info)
+        t = self.t_vals.reshape(1, 1, 1, 1, -1)
+        z = near * (1. - t) + far * t                                     # [B,N,1,1,T]
+        interval = (z[..., 1:2] - z[..., 0:1]) * d_wd.norm(dim=-1, keepdim=True)  # [B,N,S,1,1]
+        z = z.permute(0, 1, 2, 4, 3)                                      # [B,N,1,T,1]
+        ray_pts = rays_o + d_wd * z                                       # [B,N,S,T,3]
+        idx = (pts - ray_pts[..., 0:1, :]).norm(dim=-1, keepdim=True) / interval + 1e-5  # [B,N,S,1,1]
+        T = self.t_vals.shape[-1]
+        lo_i = idx.floor().long().clamp(0, T - 1)
+        hi_i = idx.ceil().long().clamp(0, T - 1)
+        viewdirs = F.normalize(d_ref if self.static_viewdirs else d_wd.squeeze(-2), dim=-1)
+        vis, w = self._march_reference_rays(ray_pts, z.squeeze(-1).expand(B, H * W, S, T), viewdirs, styles)
+        info = w if return_type == "weights" else vis
+        lo_v = torch.gather(info, 3, lo_i)
+        hi_v = torch.gather(info, 3, hi_i)
+        return torch.lerp(lo_v, hi_v, idx - lo_i).reshape(B, H, W, S, 1)
+
+    @torch.no_grad()
+    def query_hitting_probability_adapted_interval(self, wd_space_pts, ref_img_info):
+        """Same question, marching N_samples steps from the reference near plane exactly up to each
+        point and returning the last sample's weight — volume_renderer.py:1495-1621."""
+        assert wd_space_pts.ndim == 5
+        B, H, W, S = wd_space_pts.shape[:4]
+        styles = ref_img_info["pred_latents"][0]
+        near = ref_img_info["global_render_out"]["near"].reshape(B, H * W, 1, 1, 1).float()
+        pts, rays_o, d_wd, d_ref, _ = self._reference_view_rays(wd_space_pts, ref_img_info)
+        near_pts = rays_o + d_wd * near                                   # [B,N,S,1,3]
+        t = torch.linspace(0., 1., steps=self.N_samples, device=pts.device).reshape(1, 1, 1, -1, 1)
+        ray_pts = near_pts * (1 - t) + pts * t                            # [B,N,S,T,3]
+        z = (ray_pts - rays_o).norm(dim=-1)                               # [B,N,S,T]
+        viewdirs = F.normalize(d_ref if self.static_viewdirs else d_wd.squeeze(-2), dim=-1)
+        _, w = self._march_reference_rays(ray_pts, z, viewdirs, styles)
+        return w[..., -1:, :].reshape(B, H, W, S, 1)
+
     def volume_integration(self, raw, z_vals, rays_d, pts, return_eikonal=False,
                            return_surface_eikonal=False, return_mesh=True, c2w=None,
                            no_force_stop=False, **kwargs):
         """Stand-alone composite of a caller-provided `raw` (volume_renderer.py:809-943); only
-        the optional visibility queries (a17, disabled by every shipped script) use it, so it
-        stays device-side PyTorch host code.  The hot path composites inside the kernel."""
+        callers outside the fused kernel use it, so it stays device-side PyTorch host code.  The hot path composites inside the kernel."""
         if isinstance(raw, dict):
             raw = raw["raw"]
         if return_eikonal or return_surface_eikonal:

@@ -264,6 +264,25 @@ def run_grad_case(ref):
     return arrays
 
 
+def run_visibility_case(ref):
+    """query_hitting_probability_{fixed,adapted}_interval of the REAL reference
+    (volume_renderer.py:1326-1621)."""
+    cfg = P.VIS_CFG
+    torch.manual_seed(0)
+    G = build_generator(ref, cfg["size"], cfg["res"], cfg["n_samples"], cfg["seed"], cfg["variant"],
+                        full_pipeline=False)
+    R = G.renderer
+    R.local_batch = None
+    pts, info = P.visibility_case_inputs(cfg)
+    with torch.no_grad():
+        arrays = dict(
+            fixed_weights=_np(R.query_hitting_probability_fixed_interval(pts, info, "weights")),
+            fixed_visibility=_np(R.query_hitting_probability_fixed_interval(pts, info, "visibility")),
+            adapted=_np(R.query_hitting_probability_adapted_interval(pts, info)))
+    arrays["config"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+    return arrays
+
+
 def main(argv):
     if not rh.reference_available():
         raise SystemExit("reference tree not available: cannot regenerate goldens")
@@ -276,6 +295,7 @@ def main(argv):
     jobs["small_query_nfs"] = lambda: run_query_case(ref)
     jobs["ops"] = lambda: run_ops_case(ref)
     jobs["small_grad"] = lambda: run_grad_case(ref)
+    jobs["small_visibility"] = lambda: run_visibility_case(ref)
     for name, job in jobs.items():
         if want and name not in want:
             continue

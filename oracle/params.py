@@ -149,3 +149,22 @@ def make_inputs(seed, batch, n_dec_latent, res, fov_deg=6.0, dist_radius=0.12,
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.float32)
     return dict(w=f32(w), w_dec=f32(w_dec), cam_poses=f32(poses), focal=f32(focal),
                 near=f32(near), far=f32(far))
+
+
+VIS_CFG = dict(size=64, res=4, n_samples=12, n_query=5, batch=2, seed=71, variant="sharp")
+
+
+def visibility_case_inputs(cfg):
+    """Query points near the surface band + a reference view, shared by gen_golden and the tests."""
+    rng = np.random.Generator(np.random.PCG64(cfg["seed"]))
+    B, H, S = cfg["batch"], cfg["res"], cfg["n_query"]
+    pts = torch.from_numpy(rng.uniform(-0.09, 0.09, (B, H, H, S, 3)).astype(np.float32))
+    inp = make_inputs(cfg["seed"], B, 1, H)
+    poses = inp["cam_poses"]
+    R, t = poses[:, :, :3], poses[:, :, 3:]
+    extr = torch.cat([R.transpose(1, 2), -R.transpose(1, 2) @ t], 2)
+    near = inp["near"].reshape(B, 1, 1, 1).expand(B, H, H, 1).contiguous()
+    far = inp["far"].reshape(B, 1, 1, 1).expand(B, H, H, 1).contiguous()
+    info = dict(global_render_out=dict(near=near, far=far), cam_settings=dict(poses=poses, extrinsics=extr),
+                pred_latents=[inp["w"]])
+    return pts, info

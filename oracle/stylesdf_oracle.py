@@ -217,6 +217,58 @@ def sdf_query(sd, points, styles, dist_radius=0.12):
     return raw[..., 3:4].reshape(points.shape[0], -1, 1)
 
 
+def query_hitting_probability(sd, wd_space_pts, poses, extrinsics, near, far, styles, n_samples=24,
+                              mode="fixed", return_type="weights", static_viewdirs=True,
+                              offset_sampling=True, dist_radius=0.12):
+    """VolumeFeatureRenderer.query_hitting_probability_fixed_interval / _adapted_interval —
+    volume_renderer.py:1326-1493 / 1495-1621: re-march the reference camera's ray through every
+    world-space query point and read the composite (no_force_stop) at the point.
+
+    wd_space_pts [B,H,W,S,3]; poses / extrinsics [B,3,4] (camera-to-world / world-to-camera of the
+    reference view); near, far [B,H,W,1] -> [B,H,W,S,1]."""
+    B, H, W, S = wd_space_pts.shape[:4]
+    dt = wd_space_pts.dtype
+    pts = wd_space_pts.reshape(B, H * W, S, 3)
+    homo = torch.cat([pts, torch.ones_like(pts[..., :1])], -1).unsqueeze(-1)          # :1360-1362
+    w2c = torch.cat([extrinsics, torch.zeros_like(extrinsics[:, :1])], 1)
+    w2c[:, -1, -1] = 1
+    pts = pts.unsqueeze(-2)
+    rays_o = poses[..., 3:4].permute(0, 2, 1).reshape(B, 1, 1, 1, 3)
+    ref_pts = w2c.reshape(B, 1, 1, 4, 4) @ homo
+    d_ref = ref_pts[..., :3, :] / (-ref_pts[..., 2:3, :])
+    d_wd = (poses.reshape(B, 1, 1, 3, 4)[..., :3] @ d_ref).permute(0, 1, 2, 4, 3)       # B HW S 1 3
+    nr, fr = near.reshape(B, H * W, 1, 1, 1), far.reshape(B, H * W, 1, 1, 1)
+    if mode == "fixed":
+        if offset_sampling:
+            t = torch.linspace(0., 1. - 1 / n_samples, steps=n_samples, dtype=dt)
+        else:
+            t = torch.linspace(0., 1., steps=n_samples, dtype=dt)
+        z = nr * (1. - t) + fr * t                                                      # B HW 1 1 T
+        interval = (z[..., 1:2] - z[..., 0:1]) * d_wd.norm(dim=-1, keepdim=True).permute(0, 1, 2, 4, 3)
+        z = z.permute(0, 1, 2, 4, 3)
+        ray_pts = rays_o + d_wd * z
+        idx = (pts - ray_pts[..., 0:1, :]).norm(dim=-1, keepdim=True) / interval + 1e-5
+        lo = idx.floor().long().clamp(0, n_samples - 1)
+        hi = idx.ceil().long().clamp(0, n_samples - 1)
+        z = z.squeeze(-1)
+    else:
+        near_pts = rays_o + d_wd * nr
+        t = torch.linspace(0., 1., steps=n_samples, dtype=dt).reshape(1, 1, 1, -1, 1)
+        ray_pts = near_pts * (1 - t) + pts * t
+        z = (ray_pts - rays_o).norm(dim=-1)
+    d_ref = d_ref.squeeze(-1)
+    viewdirs = F.normalize(d_ref if static_viewdirs else d_wd.squeeze(3), dim=-1)
+    raw = run_network(ray_pts, viewdirs, styles, sd, dist_radius)
+    vi = volume_integration(raw, z, viewdirs, None, sd["renderer.sigmoid_beta"], no_force_stop=True,
+                            return_xyz=False)
+    if mode == "fixed":
+        info = vi["weights"] if return_type == "weights" else vi["visibility"]
+        out = torch.lerp(torch.gather(info, 3, lo), torch.gather(info, 3, hi), idx - lo)
+    else:
+        out = vi["weights"][..., -1:, :]
+    return out.reshape(B, H, W, S, 1)
+
+
 # --------------------------------------------------------------------------------------
 # StyleGAN2 ops
 # --------------------------------------------------------------------------------------

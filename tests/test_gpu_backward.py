@@ -321,3 +321,42 @@ def test_full_size_generator_backward_runs_and_is_deterministic():
     for t, u in zip(a, b):
         assert torch.isfinite(t).all() and t.abs().max() > 0
         assert torch.equal(t, u)
+
+
+def test_local_branch_feats_hook_trains_the_callers_netlocal():
+    """`local_data_batch={'feats': ...}` with a caller-supplied netLocal (SirenLocalGlobal.forward_backbone,
+    volume_renderer.py:323-336): same result as handing (alpha, beta) explicitly, and the image-space loss
+    reaches netLocal's parameters through d_local_alpha / d_local_beta (trainer.py:1611 trains them)."""
+    res, S, B, seed = 8, 12, 2, 95
+    from e3dge_b200 import model_options, rendering_options
+    from e3dge_b200.stylesdf_model import G_pred_latents
+    G = G_pred_latents(model_options(size=64, renderer_spatial_output_dim=res),
+                       rendering_options(N_samples=S, enable_local_model=True, L_pred_tex_modulations=True),
+                       full_pipeline=False).eval().cuda()
+    for p in G.parameters():
+        p.requires_grad_(False)
+
+    class NetLocal(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.local_feat_to_tex_modulations_linear = torch.nn.Linear(301, 512)
+
+    torch.manual_seed(seed)
+    net = NetLocal().cuda()
+    G.renderer.network.netLocal = net
+    inp = _cuda(P.make_inputs(seed, B, 1, res, wplus=True))
+    feats = torch.randn(B, res, res, S, 301, device="cuda") * 0.2
+    out = G.renderer(inp["cam_poses"], inp["focal"], inp["near"], inp["far"], styles=inp["w"],
+                     local_data_batch={"feats": feats})
+    with torch.no_grad():
+        mods = net.local_feat_to_tex_modulations_linear(feats)
+        ref = G.renderer(inp["cam_poses"], inp["focal"], inp["near"], inp["far"], styles=inp["w"],
+                         local_tex_modulation=tuple(torch.split(mods, 256, dim=-1)))
+    assert torch.equal(out["features"].detach(), ref["features"])
+    loss = (out["features"] ** 2).mean() + out["gen_thumb_imgs"].mean()
+    gW, gb = torch.autograd.grad(loss, [net.local_feat_to_tex_modulations_linear.weight,
+                                        net.local_feat_to_tex_modulations_linear.bias])
+    assert torch.isfinite(gW).all() and gW.abs().max() > 0 and gb.abs().max() > 0
+    # sdf does not depend on the texture modulation (volume_renderer.py:206-220)
+    assert torch.equal(out["sdf"].detach(), G.renderer(inp["cam_poses"], inp["focal"], inp["near"], inp["far"],
+                                                       styles=inp["w"])["sdf"])

@@ -474,3 +474,45 @@ def test_sdf_sample_pass_matches_oracle_at_the_returned_points():
         ref = O.sdf_query(sd, pts_world, w)
     assert out["points"].shape == (2, 3, res * res * 24) and out["sdf"].shape == (2, 1, res * res * 24)
     assert rel_linf(out["sdf"].reshape(2, -1, 1).cpu(), ref) < TOL
+
+
+def test_visibility_queries_vs_reference_fixture_and_oracle():
+    """a17: query_hitting_probability_{fixed,adapted}_interval (volume_renderer.py:1326-1621) —
+    the fixture recorded from the real reference, then a larger case against the oracle."""
+    gold, cfg = load_golden("small_visibility")
+    G, sd = _build(cfg["size"], cfg["res"], cfg["seed"], cfg["variant"], cfg["n_samples"], full_pipeline=False)
+    R = G.renderer
+    pts, info = P.visibility_case_inputs(cfg)
+    to = lambda t: t.cuda()
+    cinfo = dict(global_render_out={k: to(v) for k, v in info["global_render_out"].items()},
+                 cam_settings={k: to(v) for k, v in info["cam_settings"].items()},
+                 pred_latents=[to(info["pred_latents"][0])])
+    got = dict(fixed_weights=R.query_hitting_probability_fixed_interval(to(pts), cinfo, "weights"),
+               fixed_visibility=R.query_hitting_probability_fixed_interval(to(pts), cinfo, "visibility"),
+               adapted=R.query_hitting_probability_adapted_interval(to(pts), cinfo))
+    for k, v in got.items():
+        assert tuple(v.shape) == gold[k].shape
+        assert rel_linf(v.cpu(), gold[k]) < TOL, k
+    # 24 samples, 16x16 query rays x 7 points (more than one 4096-ray chunk is exercised by res 68 below)
+    big = dict(cfg, res=16, n_samples=24, n_query=7, seed=72)
+    G, sd = _build(64, 16, big["seed"], "sharp", 24, full_pipeline=False)
+    pts, info = P.visibility_case_inputs(big)
+    cinfo = dict(global_render_out={k: to(v) for k, v in info["global_render_out"].items()},
+                 cam_settings={k: to(v) for k, v in info["cam_settings"].items()},
+                 pred_latents=[to(info["pred_latents"][0])])
+    cs, ro = info["cam_settings"], info["global_render_out"]
+    with torch.no_grad():
+        ref = O.query_hitting_probability(sd, pts, cs["poses"], cs["extrinsics"], ro["near"], ro["far"],
+                                          info["pred_latents"][0], n_samples=24)
+    assert rel_linf(G.renderer.query_hitting_probability_fixed_interval(to(pts), cinfo).cpu(), ref) < TOL
+    # chunking over 64^2 rays: 68x68 query rays (two chunks) equal the concatenation of two halves
+    huge = dict(cfg, res=68, n_samples=12, n_query=2, seed=73, batch=1)
+    G, sd = _build(64, 16, huge["seed"], "sharp", 12, full_pipeline=False)
+    pts, info = P.visibility_case_inputs(huge)
+    cinfo = dict(global_render_out={k: to(v) for k, v in info["global_render_out"].items()},
+                 cam_settings={k: to(v) for k, v in info["cam_settings"].items()},
+                 pred_latents=[to(info["pred_latents"][0])])
+    full = G.renderer.query_hitting_probability_adapted_interval(to(pts), cinfo)
+    half = dict(cinfo, global_render_out={k: v[:, :34].contiguous() for k, v in cinfo["global_render_out"].items()})
+    part = G.renderer.query_hitting_probability_adapted_interval(to(pts[:, :34].contiguous()), half)
+    assert torch.equal(full[:, :34], part)

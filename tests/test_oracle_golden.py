@@ -163,3 +163,20 @@ def test_gradients_and_eikonal_term_vs_reference_autograd():
     sdf = O.sdf_query(sd, pts.reshape(cfg["batch"], -1, 3), inp["w"])
     eik = torch.autograd.grad(sdf.sum(), pts)[0]
     assert rel_linf(eik, gold["eikonal_term"]) < 2e-4
+
+
+def test_visibility_queries_vs_reference_fixture():
+    """query_hitting_probability_{fixed,adapted}_interval (volume_renderer.py:1326-1621)."""
+    gold, cfg = load_golden("small_visibility")
+    sd = synthetic_state_dict(cfg["size"], cfg["res"], cfg["seed"], cfg["variant"])
+    pts, info = P.visibility_case_inputs(cfg)
+    cs, ro = info["cam_settings"], info["global_render_out"]
+    args = (sd, pts, cs["poses"], cs["extrinsics"], ro["near"], ro["far"], info["pred_latents"][0])
+    with torch.no_grad():
+        got = dict(fixed_weights=O.query_hitting_probability(*args, n_samples=cfg["n_samples"]),
+                   fixed_visibility=O.query_hitting_probability(*args, n_samples=cfg["n_samples"],
+                                                                return_type="visibility"),
+                   adapted=O.query_hitting_probability(*args, n_samples=cfg["n_samples"], mode="adapted"))
+    for k, v in got.items():
+        assert tuple(v.shape) == gold[k].shape
+        assert rel_linf(v, gold[k]) < 1e-4, k
