@@ -7,14 +7,14 @@
 // (hi*hi, hi*lo, lo*hi) accumulate in fp32 in TMEM, which keeps the decoder within ~1e-5 of
 // the fp32 reference where plain bf16 operands would sit at ~1e-2 (north_star bar: 1e-3).
 //
-// Structure (persistent CTAs, one per SM, each walking 128-pixel x 128-channel output tiles; 6 warps):
+// Structure (persistent CTAs, one per SM, each walking 128-pixel x 128-channel output tiles; 10 warps):
 //   warp 0      TMA producer: 4-D tiled tensor maps over the NHWC bf16 activations
 //               (box = 64 ch x bw x bh x bb pixels, 128B swizzle, out-of-bounds = zero fill, which
 //               *is* the conv's zero padding) and 2-D maps over the K-major weights; 3-stage
 //               full/empty mbarrier ring, 64 KB per stage (A_hi, A_lo, B_hi, B_lo);
 //   warp 1      TMEM allocation (2 x 128 columns, ping-pong) + single-thread MMA issue (12 UMMAs
 //               128x128x16 per stage), tcgen05.commit releases the stage / signals the epilogue;
-//   warps 2..5  epilogue: tcgen05.ld (each warp its 32-lane quarter), demodulation + noise +
+//   warps 2..9  epilogue: tcgen05.ld (two warps per 32-lane quarter, half the columns each), demodulation + noise +
 //               bias + leaky-ReLU*sqrt(2) (StyledConv, stylesdf_model.py:494-507), fp32 NHWC store.
 #include "tcgen05.cuh"
 #include "modconv.cuh"
@@ -118,7 +118,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = 128 * 128;            // one operand tile: 128 rows x 128 B
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 + 1024;  // + barriers + align slack
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;  // two per TMEM lane quarter, each draining half of the tile's columns
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
 
 struct TcTile {
   int bw, bh, bb, tiles_x, tiles_y, tiles_b;
@@ -160,7 +161,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
     for (int s = 0; s < TC_ACC_BUFS; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], TC_EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -240,6 +241,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to warp q = warp % 4 =====
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's 32-column chunks this warp drains
     const int m = q * 32 + lane;
     const int ix = m % t.bw, iy = (m / t.bw) % t.bh, ib = m / (t.bw * t.bh);
     const float nw = (a.mode == 1) ? a.noise_w[0] : 0.f;
@@ -255,11 +257,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float* orow = a.out + (((size_t)(valid ? b : 0) * a.H + y) * a.W + x) * a.N + n0;
       mbar_wait(&acc_full[buf], use & 1);
       tc::fence_after_thread_sync();
+      constexpr int kChunksPerWarp = TC_BN / 32 / (TC_EPI_WARPS / 4);
 #pragma unroll 1
-      for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+      for (int chunk = chalf * kChunksPerWarp; chunk < (chalf + 1) * kChunksPerWarp; ++chunk) {
         float v[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
-        if (chunk == TC_BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+        if (chunk == (chalf + 1) * kChunksPerWarp - 1) {  // this warp's share is read: tell the MMA warp
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
