@@ -215,6 +215,7 @@ siren_render_bwd_tc_kernel(const __grid_constant__ RenderBwdArgs a, const __grid
     const float* pk = a.packed;
     uint32_t pd = 0;
     int cur_b = -1;
+    const bool prefetch = !(P.flags & (1u << 28));  // bit 28: measurement aid, disables the stash prefetch
 
     auto publish = [&](int j) {
       fence_proxy_async();
@@ -468,6 +469,19 @@ siren_render_bwd_tc_kernel(const __grid_constant__ RenderBwdArgs a, const __grid
         const float ds = l7 ? sm.dsdf[m] : 0.f;
         const float* la = nullptr;
         if (MODE == 0 && l7 && a.in.local_alpha && valid) la = a.in.local_alpha + (samp0 + m) * SW;
+        // The stash phases come from HBM.  While this warp would only be waiting for the GEMM, request
+        // block 0's phases into registers and pull the lines of blocks 1..3 into L2.
+        float arg0[16];
+        if (prefetch) {
+          load_args(lo, hw * 16, arg0);
+          if (valid) {
+#pragma unroll
+            for (int jj = 1; jj < 4; ++jj)
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(stash + (size_t)(lo * SW + jj * 64 + hw * 16 + i) * TCM));
+          }
+        }
         mbar_wait(&sm.d_ready, pd);
         pd ^= 1;
         tc::fence_after_thread_sync();
@@ -476,7 +490,12 @@ siren_render_bwd_tc_kernel(const __grid_constant__ RenderBwdArgs a, const __grid
         for (int j = 0; j < 4; ++j) {
           const int nb = j * 64 + hw * 16;
           float acc[16], arg[16], g[16];
-          load_args(lo, nb, arg);
+          if (prefetch && j == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) arg[i] = arg0[i];
+          } else {
+            load_args(lo, nb, arg);
+          }
           tc::tmem_ld_32x16(dsrc + j * 64, acc);
           if (l7) {
             if (la) {
