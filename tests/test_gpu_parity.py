@@ -516,3 +516,35 @@ def test_visibility_queries_vs_reference_fixture_and_oracle():
     half = dict(cinfo, global_render_out={k: v[:, :34].contiguous() for k, v in cinfo["global_render_out"].items()})
     part = G.renderer.query_hitting_probability_adapted_interval(to(pts[:, :34].contiguous()), half)
     assert torch.equal(full[:, :34], part)
+
+
+def test_generator_forward_is_cuda_graph_capturable():
+    """No host synchronisation, no allocation outside torch's allocator, every launch on the caller's
+    stream (SURVEY.md §8b "Stream"): the whole generator pass records into a CUDA graph and replays
+    bit-exactly with new inputs written into the captured buffers."""
+    G, sd = _build(64, 16, 31, "sharp")
+    a = _cuda(P.make_inputs(31, 2, decoder_layout(64, 16), 16))
+    b = _cuda(P.make_inputs(32, 2, decoder_layout(64, 16), 16))
+    buf = {k: v.clone() for k, v in a.items()}
+
+    def step():
+        with torch.no_grad():
+            return G([buf["w"], buf["w_dec"]], buf["cam_poses"], buf["focal"], buf["near"], buf["far"],
+                     input_is_latent=True, randomize_noise=False)["gen_imgs"]
+
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            out = step()
+    torch.cuda.synchronize()
+    for inp in (a, b):
+        for k in buf:
+            buf[k].copy_(inp[k])
+        g.replay()
+        torch.cuda.synchronize()
+        got = out.clone()
+        assert torch.equal(got, step())
