@@ -110,7 +110,7 @@ def build_generator(device):
 
 
 def make_inputs(rank):
-    from oracle import params as P  # deterministic synthetic latents / cameras (input generator)
+    import synthetic_inputs as P  # deterministic synthetic latents / cameras (input generator)
     from helpers import decoder_layout
     return P.make_inputs(SEED + rank, BATCH, decoder_layout(SIZE, RES), RES)
 

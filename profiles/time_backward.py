@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 from e3dge_b200 import model_options, rendering_options  # noqa: E402
 from e3dge_b200.stylesdf_model import G_pred_latents  # noqa: E402
-from oracle import params as P  # noqa: E402  (inputs only)
+import synthetic_inputs as P  # noqa: E402
 
 
 def timed(fn, n=10, warm=3):

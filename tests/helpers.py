@@ -5,7 +5,7 @@ import os
 import numpy as np
 import torch
 
-from oracle import params as P
+import synthetic_inputs as P
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
