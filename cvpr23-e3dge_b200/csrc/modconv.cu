@@ -19,6 +19,9 @@
 //     the decoder's real shapes (power-of-two maps, Cin % 64 == 0, N % 128 == 0);
 //   * CUDA cores (this file): exact-fp32 FFMA implicit GEMM for every other shape, and the
 //     numerical baseline the tensor-core path is tested against.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
 #include "modconv.cuh"
 
 namespace e3 {
@@ -250,6 +253,9 @@ struct Col2imArgs {
   int64_t noise_bstride;
   const float* noise_w;
   const float* act_bias;  // NULL: bare modulated conv (d * blur(convT)), no noise / bias / act
+  // banded run (L2-resident G, see e3_styled_conv3x3_up_fwd): this launch produces the outputs of input
+  // rows [row0, row1) of the flattened (b, y) row index, and g holds input rows from g_row_base on
+  int row0, row1, g_row_base;
 };
 
 // One thread = a 2x2 output block (rows 2y,2y+1; cols 2x,2x+1) x 4 channels.  Along one axis the
@@ -268,13 +274,14 @@ __device__ __forceinline__ float c2i_coef(int phase, int d, int k) {
 __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_constant__ Col2imArgs a) {
   const int c4n = a.cout >> 2;
   const int OW = 2 * a.W, OH = 2 * a.H;
-  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
+  const int64_t total = (int64_t)(a.row1 - a.row0) * a.W * c4n;
   const bool linear = a.act_bias == nullptr;
+  const float* g = a.g - (int64_t)a.g_row_base * a.W * 9 * a.cout;
   const float nw = linear ? 0.f : a.noise_w[0];
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int o = (int)(idx % c4n) * 4;
-    int64_t t = idx / c4n;
+    int64_t t = idx / c4n + (int64_t)a.row0 * a.W;
     const int x = (int)(t % a.W);
     t /= a.W;
     const int y = (int)(t % a.H);
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_const
             const float cx0 = c2i_coef(0, dx, kx), cx1 = c2i_coef(1, dx, kx);
             if (cx0 == 0.f && cx1 == 0.f) continue;
             const float4 gv = *reinterpret_cast<const float4*>(
-                a.g + ((((size_t)b * a.H + iy) * a.W + ix) * 9 + ky * 3 + kx) * a.cout + o);
+                g + ((((size_t)b * a.H + iy) * a.W + ix) * 9 + ky * 3 + kx) * a.cout + o);
             const float w00 = cy0 * cx0, w01 = cy0 * cx1, w10 = cy1 * cx0, w11 = cy1 * cx1;
             if (w00 != 0.f) acc[0][0].x = fmaf(w00, gv.x, acc[0][0].x), acc[0][0].y = fmaf(w00, gv.y, acc[0][0].y),
                             acc[0][0].z = fmaf(w00, gv.z, acc[0][0].z), acc[0][0].w = fmaf(w00, gv.w, acc[0][0].w);
@@ -513,6 +520,13 @@ extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int u
                              const_cast<void*>(packed_bf16_part(packed, cout, cin)), as_stream(stream));
 }
 
+// Target size of one band of the up-conv's G intermediate (E3DGE_UPCONV_BAND_KB overrides; 0 = one
+// pass over the whole batch).  40 MB holds one 64x64x(9*256) image / half a 128x128x(9*128) image.
+static int64_t upconv_band_bytes() {
+  const char* e = getenv("E3DGE_UPCONV_BAND_KB");
+  return (int64_t)(e ? atoi(e) : 40 * 1024) << 10;
+}
+
 static bool use_tensor_cores(uint32_t flags, int batch, int h, int w, int cin, int n) {
   if (flags & E3_CONV_FP32_CUDA_CORES) return false;
   return tc_conv_supported(batch, h, w, cin, n);
@@ -586,9 +600,44 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
   const bool tcore = use_tensor_cores(flags, batch, h, w, cin, a.N);
   E3_REQUIRE(tcore || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
              "e3_styled_conv3x3_up_fwd: E3_CONV_TENSOR_CORES requested for an unsupported shape");
+  Col2imArgs c{};
+  c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
+  c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;
+  c.act_bias = act_bias;
+  c.row0 = 0, c.row1 = batch * h, c.g_row_base = 0;
   if (tcore) {
     char* after_g = static_cast<char*>(scratch) + (size_t)batch * h * w * 9 * cout * sizeof(float);
     void* split = reinterpret_cast<void*>(((uintptr_t)after_g + 255) & ~(uintptr_t)255);
+    // G = xs * W is the largest tensor of the decoder (9*cout floats per input pixel: 302 / 604 MB for
+    // the two up-convs at batch 8) and is written once and read once.  Run GEMM and col2im band by
+    // band over the flattened (b, y) rows, each band's G (plus one halo row either side) reusing the
+    // SAME buffer, small enough to stay in the 126 MB L2: the G traffic never reaches HBM.
+    const int rm = w >= 128 ? 1 : 128 / w;          // rows per 128-pixel GEMM tile
+    const int64_t row_bytes = (int64_t)w * 9 * cout * sizeof(float);
+    const int rows_total = batch * h;
+    int band = (int)(upconv_band_bytes() / row_bytes);
+    if (band >= h) band = band / h * h;                                  // whole images
+    else if (band > 0) band = h / ((h + band - 1) / band);               // equal parts of an image
+    if (band > 0 && band < rows_total && rows_total % rm == 0 && (w % 128 == 0 || w * rm == 128)) {
+      if ((rc = tc_conv_split(a, split, as_stream(stream)))) return rc;
+      const __nv_bfloat16* xs_hi = static_cast<const __nv_bfloat16*>(split);
+      const __nv_bfloat16* xs_lo = xs_hi + (size_t)batch * h * w * cin;
+      const int64_t total_band = (int64_t)band * w * (cout / 4);
+      for (int r0 = 0; r0 < rows_total; r0 += band) {
+        const int r1 = r0 + band < rows_total ? r0 + band : rows_total;
+        // halo rows only inside the image the band's edge rows belong to
+        int g0 = (r0 % h) ? r0 - 1 : r0, g1 = (r1 % h) ? r1 + 1 : r1;
+        g0 = g0 / rm * rm, g1 = (g1 + rm - 1) / rm * rm;
+        const size_t off = (size_t)g0 * w * cin;
+        if ((rc = tc_gemm_rows_presplit(xs_hi + off, xs_lo + off, (int64_t)(g1 - g0) * w, cin, a.N,
+                                        packed_bf16_part(wpacked, cout, cin), a.out, as_stream(stream))))
+          return rc;
+        c.row0 = r0, c.row1 = r1, c.g_row_base = g0;
+        col2im_blur_act_kernel<<<grid_cap((total_band + 255) / 256), 256, 0, as_stream(stream)>>>(c);
+      }
+      E3_CUDA(cudaGetLastError());
+      return E3_OK;
+    }
     rc = tc_conv_launch(a, 1, packed_bf16_part(wpacked, cout, cin), split, as_stream(stream));
     if (rc) return rc;
   } else {
@@ -597,10 +646,6 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
     conv_gemm_ffma_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a);
     E3_CUDA(cudaGetLastError());
   }
-  Col2imArgs c{};
-  c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
-  c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;
-  c.act_bias = act_bias;
   const int64_t total = (int64_t)batch * h * w * (cout / 4);  // one thread per 2x2 output block x 4 ch
   col2im_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(c);
   E3_CUDA(cudaGetLastError());

@@ -88,6 +88,68 @@ __device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float*
   *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes' worth of work) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// sin of the pair gamma*acc + beta' (same arithmetic as sin_mufu_reduced, two lanes per instruction)
+__device__ __forceinline__ void film_sin2(f32x2 acc, f32x2 g, f32x2 bt, float& s0, float& s1, f32x2& arg) {
+  const f32x2 kInv = pk2(0.159154943f, 0.159154943f), kMagic = pk2(12582912.0f, 12582912.0f);
+  const f32x2 kNegMagic = pk2(-12582912.0f, -12582912.0f), kC1 = pk2(-6.28125f, -6.28125f);
+  const f32x2 kC2 = pk2(-1.9353071795864769e-3f, -1.9353071795864769e-3f);
+  arg = fma2(g, acc, bt);
+  const f32x2 jm = fma2(arg, kInv, kMagic);
+  const f32x2 j = add2(jm, kNegMagic);
+  f32x2 r = fma2(j, kC1, arg);
+  r = fma2(j, kC2, r);
+  float r0, r1;
+  unpk2(r, r0, r1);
+  s0 = __sinf(r0);
+  s1 = __sinf(r1);
+}
+// hi/lo bf16 split of a pair with the subtraction packed
+__device__ __forceinline__ void split_pair_bf16_x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  const f32x2 h = pk2u(hi << 16, hi & 0xffff0000u);
+  const f32x2 d = fma2(h, pk2(-1.f, -1.f), pk2(v0, v1));  // v - h, exact
+  float d0, d1;
+  unpk2(d, d0, d1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+}
+template <int EPI>
+__device__ __forceinline__ void store_a8_v(SmemTC& sm, int m, int n0, const float* v) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (EPI & 1) split_pair_bf16_x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    else split_pair_bf16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  }
+  const uint32_t off = (uint32_t)(n0 >> 6) * A_KBLOCK_BYTES + a_chunk_off(m, (n0 & 63) >> 3);
+  *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 // CL = thread-block cluster size.  The weight stream is identical for every tile, so the CTAs of a
 // cluster share it: each fetches 1/CL of every 16 KB weight tile and TMA-multicasts it into all CL
 // rings (cp.async.bulk ... .multicast::cluster).  A ring stage is recycled when every CTA of the
@@ -99,7 +161,9 @@ __device__ __forceinline__ void store_a8(SmemTC& sm, int m, int n0, const float*
 // STASH: training build that also writes the pre-sin phases for e3_render_bwd (a compile-time switch:
 // even predicated off, the per-element address arithmetic would cost the inference build ~3
 // instruction slots per element).
-template <int MODE, int CL, bool STASH>
+// EPI: epilogue code variant of the hidden layers (bit 0: packed f32x2 FiLM / range reduction / split
+// and the FiLM rows fetched while the tcgen05.ld is in flight).
+template <int MODE, int CL, bool STASH, int EPI>
 // 18 warps: one scheduler holds 5 of them, so 16384 / (5 * 32) = 102 -> 96 registers per thread
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ CUtensorMap wmap,
@@ -395,17 +459,50 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           float acc[16];
-          tc::tmem_ld_32x16(dsrc + j * 64, acc);
+          float4 fg[4], fb[4];
+          if (EPI & 1) {
+            uint32_t accr[16];
+            tc::tmem_ld_32x16_issue(dsrc + j * 64, accr);
+            const float4* gp = reinterpret_cast<const float4*>(&sm.film[l][0][j * 64 + hw * 16]);
+            const float4* bp = reinterpret_cast<const float4*>(&sm.film[l][1][j * 64 + hw * 16]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fg[i] = gp[i], fb[i] = bp[i];
+            tc::tmem_ld_wait16(accr);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(accr[i]);
+          } else {
+            tc::tmem_ld_32x16(dsrc + j * 64, acc);
+          }
+          if (tr && l == 3) a.trace[384 + j * 8] = clock64();
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const int n0 = j * 64 + hw * 16 + g8 * 8;
             float v[8];
+            if (EPI & 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
-              if (STASH && stash) stash[(size_t)(l * SW + n0 + i) * TCM] = arg;
-              v[i] = no_sin ? arg * 1e-3f : sin_mufu_reduced(arg);
+              for (int h = 0; h < 2; ++h) {
+                const float4 g4 = fg[g8 * 2 + h], b4 = fb[g8 * 2 + h];
+                const int c = g8 * 8 + h * 4;
+                f32x2 a0, a1;
+                film_sin2(pk2(acc[c], acc[c + 1]), pk2(g4.x, g4.y), pk2(b4.x, b4.y), v[h * 4], v[h * 4 + 1], a0);
+                film_sin2(pk2(acc[c + 2], acc[c + 3]), pk2(g4.z, g4.w), pk2(b4.z, b4.w), v[h * 4 + 2], v[h * 4 + 3], a1);
+                if (STASH && stash) {
+                  float t0, t1, t2, t3;
+                  unpk2(a0, t0, t1);
+                  unpk2(a1, t2, t3);
+                  float* sp = stash + (size_t)(l * SW + n0 + h * 4) * TCM;
+                  sp[0] = t0, sp[TCM] = t1, sp[2 * TCM] = t2, sp[3 * TCM] = t3;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
+                if (STASH && stash) stash[(size_t)(l * SW + n0 + i) * TCM] = arg;
+                v[i] = no_sin ? arg * 1e-3f : sin_mufu_reduced(arg);
+              }
             }
+            if (tr && l == 3) a.trace[384 + j * 8 + 1 + g8 * 2] = clock64();
             if (last) {
               // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
 #pragma unroll
@@ -417,9 +514,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               }
             }
             if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
-            if (feed) store_a8(sm, m, n0, v);
+            if (feed) store_a8_v<EPI>(sm, m, n0, v);
+            if (tr && l == 3) a.trace[384 + j * 8 + 2 + g8 * 2] = clock64();
           }
           if (feed) publish(j);
+          if (tr && l == 3) a.trace[384 + j * 8 + 5] = clock64();
           if (tr) a.trace[l * 8 + 1 + j] = clock64();
         }
         if (!feed) tc::fence_before_thread_sync();
@@ -600,11 +699,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int MODE, int CL, bool STASH = false>
+template <int MODE, int CL, bool STASH = false, int EPI = 0>
 static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
   static thread_local bool attr_set = false;
   const int smem_bytes = (int)sizeof(SmemTC) + 1024;
-  auto* fn = siren_render_tc_kernel<MODE, CL, STASH>;
+  auto* fn = siren_render_tc_kernel<MODE, CL, STASH, EPI>;
   if (!attr_set) {
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
@@ -666,6 +765,12 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
     a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
   const int cl = render_cluster_size();
   if (a.stash) return mode == 0 ? launch_tc_variant<0, 1, true>(a, stream) : launch_tc_variant<1, 1, true>(a, stream);
+  static int epi = -1;
+  if (epi < 0) {
+    const char* e = getenv("E3DGE_RENDER_EPI");  // measurement aid: epilogue code variant
+    epi = e ? atoi(e) : 0;
+  }
+  if (mode == 0 && cl == 1 && epi == 1) return launch_tc_variant<0, 1, false, 1>(a, stream);
   if (mode == 0) {
     if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
     if (cl == 2) return launch_tc_variant<0, 2>(a, stream);

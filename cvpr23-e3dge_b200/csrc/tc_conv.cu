@@ -322,14 +322,35 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
   const size_t n_act = (size_t)a.B * a.H * a.W * a.Cin;
   __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
   __nv_bfloat16* xs_lo = xs_hi + n_act;
-  {
-    const int64_t nv = (int64_t)(n_act / 8);
-    int blocks = (int)((nv + 255) / 256);
-    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-    modulate_split_kernel<<<blocks, 256, 0, stream>>>(a.x, a.s, xs_hi, xs_lo, nv, a.H * a.W, a.Cin);
-    E3_CUDA(cudaGetLastError());
-  }
+  int rc = tc_conv_split(a, split_scratch, stream);
+  if (rc) return rc;
   return tc_conv_launch_presplit(a, taps, packed_bf16, xs_hi, xs_lo, stream);
+}
+
+int tc_conv_split(const ConvGemmArgs& a, void* split_scratch, cudaStream_t stream) {
+  const size_t n_act = (size_t)a.B * a.H * a.W * a.Cin;
+  __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
+  __nv_bfloat16* xs_lo = xs_hi + n_act;
+  const int64_t nv = (int64_t)(n_act / 8);
+  int blocks = (int)((nv + 255) / 256);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  modulate_split_kernel<<<blocks, 256, 0, stream>>>(a.x, a.s, xs_hi, xs_lo, nv, a.H * a.W, a.Cin);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+static int tc_conv_launch_checked(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
+                                  const void* xs_lo, cudaStream_t stream);
+
+// Plain GEMM G[m][n] = sum_ci xs[m][ci] * Wk[n][ci] over a run of m_rows pixels (a multiple of 128):
+// the 1-tap kernel on the run viewed as one image of m_rows/128 rows x 128 pixels.
+int tc_gemm_rows_presplit(const void* xs_hi, const void* xs_lo, int64_t m_rows, int Cin, int N,
+                          const void* packed_bf16, float* out, cudaStream_t stream) {
+  E3_REQUIRE(m_rows > 0 && m_rows % TC_BM == 0 && m_rows / TC_BM < (1 << 24) && Cin % TC_BK == 0 && N % TC_BN == 0,
+             E3_ERR_UNSUPPORTED, "tensor-core GEMM: unsupported shape M=%lld Cin=%d N=%d", (long long)m_rows, Cin, N);
+  ConvGemmArgs a{};
+  a.out = out, a.B = 1, a.H = (int)(m_rows / TC_BM), a.W = TC_BM, a.Cin = Cin, a.N = N, a.mode = 0;
+  return tc_conv_launch_checked(a, 1, packed_bf16, xs_hi, xs_lo, stream);
 }
 
 int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
@@ -338,6 +359,11 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
              "tensor-core conv: unsupported shape B=%d H=%d W=%d Cin=%d N=%d (needs power-of-two "
              "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0)", a.B, a.H, a.W, a.Cin, a.N);
   E3_REQUIRE(!a.planar || taps == 9, E3_ERR_BAD_ARG, "tensor-core conv: planar operands need 9 taps");
+  return tc_conv_launch_checked(a, taps, packed_bf16, xs_hi, xs_lo, stream);
+}
+
+static int tc_conv_launch_checked(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
+                                  const void* xs_lo, cudaStream_t stream) {
   TcTile t;
   t.bw = a.W < 128 ? a.W : 128;
   t.bh = (128 / t.bw) < a.H ? (128 / t.bw) : a.H;

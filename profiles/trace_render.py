@@ -27,3 +27,9 @@ for l in range(8):
     mi = [rel(t[256 + l * 16 + kb * 4 + 3]) for kb in range(4)]
     print(f"L{l}  {comp[0]}  {comp[1:]}  ||  G{l}: {mw}  {mi}")
 print("view-layer d_ready seen:", rel(t[64]), " tile end:", rel(t[65]))
+# inside layer 3 (warp 2 lane 0): per 64-channel block, cycles since the layer's d_ready was seen
+base = t[3 * 8]
+if t[384]:
+    print("layer 3 block j: tcgen05.ld landed | first 8 ch computed | stored | second 8 computed | stored | published")
+    for j in range(4):
+        print(f"  j{j}  ", [t[384 + j * 8 + k] - base for k in range(6)])
