@@ -19,9 +19,6 @@
 //     the decoder's real shapes (power-of-two maps, Cin % 64 == 0, N % 128 == 0);
 //   * CUDA cores (this file): exact-fp32 FFMA implicit GEMM for every other shape, and the
 //     numerical baseline the tensor-core path is tested against.
-#include <cuda_bf16.h>
-#include <stdlib.h>
-
 #include "modconv.cuh"
 
 namespace e3 {
@@ -253,9 +250,6 @@ struct Col2imArgs {
   int64_t noise_bstride;
   const float* noise_w;
   const float* act_bias;  // NULL: bare modulated conv (d * blur(convT)), no noise / bias / act
-  // banded run (L2-resident G, see e3_styled_conv3x3_up_fwd): this launch produces the outputs of input
-  // rows [row0, row1) of the flattened (b, y) row index, and g holds input rows from g_row_base on
-  int row0, row1, g_row_base;
 };
 
 // One thread = a 2x2 output block (rows 2y,2y+1; cols 2x,2x+1) x 4 channels.  Along one axis the
@@ -274,14 +268,13 @@ __device__ __forceinline__ float c2i_coef(int phase, int d, int k) {
 __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_constant__ Col2imArgs a) {
   const int c4n = a.cout >> 2;
   const int OW = 2 * a.W, OH = 2 * a.H;
-  const int64_t total = (int64_t)(a.row1 - a.row0) * a.W * c4n;
+  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
   const bool linear = a.act_bias == nullptr;
-  const float* g = a.g - (int64_t)a.g_row_base * a.W * 9 * a.cout;
   const float nw = linear ? 0.f : a.noise_w[0];
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int o = (int)(idx % c4n) * 4;
-    int64_t t = idx / c4n + (int64_t)a.row0 * a.W;
+    int64_t t = idx / c4n;
     const int x = (int)(t % a.W);
     t /= a.W;
     const int y = (int)(t % a.H);
@@ -308,7 +301,7 @@ __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_const
             const float cx0 = c2i_coef(0, dx, kx), cx1 = c2i_coef(1, dx, kx);
             if (cx0 == 0.f && cx1 == 0.f) continue;
             const float4 gv = *reinterpret_cast<const float4*>(
-                g + ((((size_t)b * a.H + iy) * a.W + ix) * 9 + ky * 3 + kx) * a.cout + o);
+                a.g + ((((size_t)b * a.H + iy) * a.W + ix) * 9 + ky * 3 + kx) * a.cout + o);
             const float w00 = cy0 * cx0, w01 = cy0 * cx1, w10 = cy1 * cx0, w11 = cy1 * cx1;
             if (w00 != 0.f) acc[0][0].x = fmaf(w00, gv.x, acc[0][0].x), acc[0][0].y = fmaf(w00, gv.y, acc[0][0].y),
                             acc[0][0].z = fmaf(w00, gv.z, acc[0][0].z), acc[0][0].w = fmaf(w00, gv.w, acc[0][0].w);
@@ -320,6 +313,91 @@ __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_const
                             acc[1][1].z = fmaf(w11, gv.z, acc[1][1].z), acc[1][1].w = fmaf(w11, gv.w, acc[1][1].w);
           }
         }
+      }
+    }
+    const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!linear) bv = *reinterpret_cast<const float4*>(a.act_bias + o);
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int Y = 2 * y + py, X = 2 * x + px;
+        const float4 s4 = acc[py][px];
+        float v[4] = {s4.x * dv.x, s4.y * dv.y, s4.z * dv.z, s4.w * dv.w};
+        if (!linear) {
+          const float nz = nw * a.noise[(size_t)b * a.noise_bstride + (size_t)Y * OW + X];
+          v[0] = fmaf(s4.x, dv.x, nz) + bv.x, v[1] = fmaf(s4.y, dv.y, nz) + bv.y;
+          v[2] = fmaf(s4.z, dv.z, nz) + bv.z, v[3] = fmaf(s4.w, dv.w, nz) + bv.w;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) v[qq] = (v[qq] > 0.f ? v[qq] : 0.2f * v[qq]) * kSqrt2;
+        }
+        *reinterpret_cast<float4*>(a.y + (((size_t)b * OH + Y) * OW + X) * a.cout + o) =
+            make_float4(v[0], v[1], v[2], v[3]);
+      }
+  }
+}
+
+// ---- 4x4 blur + StyledConv epilogue over the parity-phase transposed-conv output ---------------
+// T[P,Q] (P in [0,2H], Q in [0,2W]) lives as four phase planes on the padded grid (tc_conv.cu):
+//   T[2i+py, 2j+px, o] = t[(py*2+px)][(b*(H+1) + i)*(W+1) + j][o]
+// out[Y,X,o] = lrelu( d * sum_{a,c<4} kb[a] kb[c] T[Y+a-1, X+c-1, o] + noise + bias ) * sqrt2, kb = [1,3,3,1]/4.
+// One thread = a 2x2 output block x 4 channels: T rows 2y-1 .. 2y+3 = (odd,y-1) (even,y) (odd,y) (even,y+1)
+// (odd,y+1), same along x: 25 vector reads for 16 outputs.
+struct UpBlurArgs {
+  const float* t;  // [4][Mp][cout]
+  float* y;        // [B,2H,2W,cout]
+  int B, H, W, cout;
+  const float* d;
+  const float* noise;
+  int64_t noise_bstride;
+  const float* noise_w;
+  const float* act_bias;  // NULL: bare modulated conv
+};
+
+__global__ void __launch_bounds__(256) upconv_blur_act_kernel(const __grid_constant__ UpBlurArgs a) {
+  const int c4n = a.cout >> 2;
+  const int OW = 2 * a.W, OH = 2 * a.H, Wp = a.W + 1, Hp = a.H + 1;
+  const int64_t Mp = (int64_t)a.B * Hp * Wp;
+  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
+  const bool linear = a.act_bias == nullptr;
+  const float nw = linear ? 0.f : a.noise_w[0];
+  const float w0[5] = {.25f, .75f, .75f, .25f, 0.f};  // weight of T row r (of 5) in output row 2y
+  const float w1[5] = {0.f, .25f, .75f, .75f, .25f};  // ... in output row 2y+1
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % c4n) * 4;
+    int64_t t = idx / c4n;
+    const int x = (int)(t % a.W);
+    t /= a.W;
+    const int y = (int)(t % a.H);
+    const int b = (int)(t / a.H);
+    float4 acc[2][2];
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) acc[py][px] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int pr = (r & 1) ^ 1;           // rows alternate odd, even, odd, even, odd
+      const int i = y + ((r + 1) >> 1) - 1;  // y-1, y, y, y+1, y+1
+      if (i < 0 || i >= a.H + (pr ? 0 : 1)) continue;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int pc = (c & 1) ^ 1;
+        const int j = x + ((c + 1) >> 1) - 1;
+        if (j < 0 || j >= a.W + (pc ? 0 : 1)) continue;
+        const float4 tv = *reinterpret_cast<const float4*>(
+            a.t + ((size_t)(pr * 2 + pc) * Mp + ((size_t)b * Hp + i) * Wp + j) * a.cout + o);
+        const float k00 = w0[r] * w0[c], k01 = w0[r] * w1[c], k10 = w1[r] * w0[c], k11 = w1[r] * w1[c];
+        if (k00 != 0.f) acc[0][0].x = fmaf(k00, tv.x, acc[0][0].x), acc[0][0].y = fmaf(k00, tv.y, acc[0][0].y),
+                        acc[0][0].z = fmaf(k00, tv.z, acc[0][0].z), acc[0][0].w = fmaf(k00, tv.w, acc[0][0].w);
+        if (k01 != 0.f) acc[0][1].x = fmaf(k01, tv.x, acc[0][1].x), acc[0][1].y = fmaf(k01, tv.y, acc[0][1].y),
+                        acc[0][1].z = fmaf(k01, tv.z, acc[0][1].z), acc[0][1].w = fmaf(k01, tv.w, acc[0][1].w);
+        if (k10 != 0.f) acc[1][0].x = fmaf(k10, tv.x, acc[1][0].x), acc[1][0].y = fmaf(k10, tv.y, acc[1][0].y),
+                        acc[1][0].z = fmaf(k10, tv.z, acc[1][0].z), acc[1][0].w = fmaf(k10, tv.w, acc[1][0].w);
+        if (k11 != 0.f) acc[1][1].x = fmaf(k11, tv.x, acc[1][1].x), acc[1][1].y = fmaf(k11, tv.y, acc[1][1].y),
+                        acc[1][1].z = fmaf(k11, tv.z, acc[1][1].z), acc[1][1].w = fmaf(k11, tv.w, acc[1][1].w);
       }
     }
     const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);
@@ -520,23 +598,21 @@ extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int u
                              const_cast<void*>(packed_bf16_part(packed, cout, cin)), as_stream(stream));
 }
 
-// Target size of one band of the up-conv's G intermediate (E3DGE_UPCONV_BAND_KB overrides; 0 = one
-// pass over the whole batch).  40 MB holds one 64x64x(9*256) image / half a 128x128x(9*128) image.
-static int64_t upconv_band_bytes() {
-  const char* e = getenv("E3DGE_UPCONV_BAND_KB");
-  return (int64_t)(e ? atoi(e) : 40 * 1024) << 10;
-}
-
 static bool use_tensor_cores(uint32_t flags, int batch, int h, int w, int cin, int n) {
   if (flags & E3_CONV_FP32_CUDA_CORES) return false;
   return tc_conv_supported(batch, h, w, cin, n);
 }
 
-// scratch = [G (upsample only): B*H*W*9*cout fp32] [xs_hi | xs_lo: B*H*W*cin bf16 each]
+// scratch, plain conv:  [xs_hi | xs_lo: B*H*W*cin bf16 each]
+// upsampling conv:      [G: B*H*W*9*cout fp32 (CUDA-core path)  |  T: 4*B*(H+1)*(W+1)*cout fp32 (tensor-core
+//                        path, always smaller)] [xs_hi | xs_lo on the zero-padded grid B*(H+1)*(W+1)*cin]
 extern "C" size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout,
                                                int upsample) {
-  const size_t g = upsample ? (size_t)batch * h * w * 9 * cout * sizeof(float) : 0;
-  return g + tc_conv_split_bytes(batch, h, w, cin) + 256;
+  if (!upsample) return tc_conv_split_bytes(batch, h, w, cin) + 256;
+  size_t g = (size_t)batch * h * w * 9 * cout * sizeof(float);
+  const size_t t = tc_upconv_t_bytes(batch, h, w, cout);
+  if (t > g) g = t;
+  return g + tc_upconv_split_bytes(batch, h, w, cin) + 256;
 }
 
 static int check_conv_shapes(const char* who, int batch, int h, int w, int cin, int cout) {
@@ -597,55 +673,38 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
   a.x = x, a.s = s, a.wg = static_cast<const float*>(wpacked), a.out = static_cast<float*>(scratch);
   a.B = batch, a.H = h, a.W = w, a.Cin = cin, a.N = 9 * cout;
   a.mode = 0;
-  const bool tcore = use_tensor_cores(flags, batch, h, w, cin, a.N);
+  const bool tcore = !(flags & E3_CONV_FP32_CUDA_CORES) && tc_upconv_supported(batch, h, w, cin, cout);
   E3_REQUIRE(tcore || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
              "e3_styled_conv3x3_up_fwd: E3_CONV_TENSOR_CORES requested for an unsupported shape");
-  Col2imArgs c{};
-  c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
-  c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;
-  c.act_bias = act_bias;
-  c.row0 = 0, c.row1 = batch * h, c.g_row_base = 0;
   if (tcore) {
-    char* after_g = static_cast<char*>(scratch) + (size_t)batch * h * w * 9 * cout * sizeof(float);
-    void* split = reinterpret_cast<void*>(((uintptr_t)after_g + 255) & ~(uintptr_t)255);
-    // G = xs * W is the largest tensor of the decoder (9*cout floats per input pixel: 302 / 604 MB for
-    // the two up-convs at batch 8) and is written once and read once.  Run GEMM and col2im band by
-    // band over the flattened (b, y) rows, each band's G (plus one halo row either side) reusing the
-    // SAME buffer, small enough to stay in the 126 MB L2: the G traffic never reaches HBM.
-    const int rm = w >= 128 ? 1 : 128 / w;          // rows per 128-pixel GEMM tile
-    const int64_t row_bytes = (int64_t)w * 9 * cout * sizeof(float);
-    const int rows_total = batch * h;
-    int band = (int)(upconv_band_bytes() / row_bytes);
-    if (band >= h) band = band / h * h;                                  // whole images
-    else if (band > 0) band = h / ((h + band - 1) / band);               // equal parts of an image
-    if (band > 0 && band < rows_total && rows_total % rm == 0 && (w % 128 == 0 || w * rm == 128)) {
-      if ((rc = tc_conv_split(a, split, as_stream(stream)))) return rc;
-      const __nv_bfloat16* xs_hi = static_cast<const __nv_bfloat16*>(split);
-      const __nv_bfloat16* xs_lo = xs_hi + (size_t)batch * h * w * cin;
-      const int64_t total_band = (int64_t)band * w * (cout / 4);
-      for (int r0 = 0; r0 < rows_total; r0 += band) {
-        const int r1 = r0 + band < rows_total ? r0 + band : rows_total;
-        // halo rows only inside the image the band's edge rows belong to
-        int g0 = (r0 % h) ? r0 - 1 : r0, g1 = (r1 % h) ? r1 + 1 : r1;
-        g0 = g0 / rm * rm, g1 = (g1 + rm - 1) / rm * rm;
-        const size_t off = (size_t)g0 * w * cin;
-        if ((rc = tc_gemm_rows_presplit(xs_hi + off, xs_lo + off, (int64_t)(g1 - g0) * w, cin, a.N,
-                                        packed_bf16_part(wpacked, cout, cin), a.out, as_stream(stream))))
-          return rc;
-        c.row0 = r0, c.row1 = r1, c.g_row_base = g0;
-        col2im_blur_act_kernel<<<grid_cap((total_band + 255) / 256), 256, 0, as_stream(stream)>>>(c);
-      }
-      E3_CUDA(cudaGetLastError());
-      return E3_OK;
-    }
-    rc = tc_conv_launch(a, 1, packed_bf16_part(wpacked, cout, cin), split, as_stream(stream));
+    // four parity-phase convolutions accumulate the transposed conv in TMEM -> T, then blur + epilogue
+    size_t t_bytes = tc_upconv_t_bytes(batch, h, w, cout);
+    const size_t g_bytes = (size_t)batch * h * w * 9 * cout * sizeof(float);
+    if (g_bytes > t_bytes) t_bytes = g_bytes;
+    char* after_t = static_cast<char*>(scratch) + t_bytes;
+    void* split = reinterpret_cast<void*>(((uintptr_t)after_t + 255) & ~(uintptr_t)255);
+    float* t_out = static_cast<float*>(scratch);
+    rc = tc_upconv_phase_launch(x, s, batch, h, w, cin, cout, packed_bf16_part(wpacked, cout, cin), split,
+                                t_out, as_stream(stream));
     if (rc) return rc;
-  } else {
+    UpBlurArgs u{};
+    u.t = t_out, u.y = y, u.B = batch, u.H = h, u.W = w, u.cout = cout;
+    u.d = d, u.noise = noise, u.noise_bstride = noise_batch_stride, u.noise_w = noise_w, u.act_bias = act_bias;
+    const int64_t total = (int64_t)batch * h * w * (cout / 4);
+    upconv_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(u);
+    E3_CUDA(cudaGetLastError());
+    return E3_OK;
+  }
+  {
     const int64_t M = (int64_t)batch * h * w;
     dim3 grid((unsigned)((M + CG_BM - 1) / CG_BM), (a.N + CG_BN - 1) / CG_BN);
     conv_gemm_ffma_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a);
     E3_CUDA(cudaGetLastError());
   }
+  Col2imArgs c{};
+  c.g = static_cast<const float*>(scratch), c.y = y, c.B = batch, c.H = h, c.W = w, c.cout = cout;
+  c.d = d, c.noise = noise, c.noise_bstride = noise_batch_stride, c.noise_w = noise_w;
+  c.act_bias = act_bias;
   const int64_t total = (int64_t)batch * h * w * (cout / 4);  // one thread per 2x2 output block x 4 ch
   col2im_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(c);
   E3_CUDA(cudaGetLastError());

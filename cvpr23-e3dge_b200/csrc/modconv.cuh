@@ -33,11 +33,13 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
 // same without the modulate+split pass: xs_hi / xs_lo are the caller's bf16 operand halves
 int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
                             const void* xs_lo, cudaStream_t stream);
-// the modulate + hi/lo split pass alone: split_scratch <- [xs_hi | xs_lo]
-int tc_conv_split(const ConvGemmArgs& a, void* split_scratch, cudaStream_t stream);
-// G[m][n] = sum_ci xs[m][ci] * Wk[n][ci] over m_rows (% 128 == 0) consecutive pixels of pre-split operands
-int tc_gemm_rows_presplit(const void* xs_hi, const void* xs_lo, int64_t m_rows, int Cin, int N,
-                          const void* packed_bf16, float* out, cudaStream_t stream);
+// upsampling conv as four parity-phase convolutions of a zero-padded flat pixel grid (tc_conv.cu):
+// T [4][B*(H+1)*(W+1)][cout] = conv_transpose2d(x*s, W, stride 2) by output parity
+bool tc_upconv_supported(int B, int H, int W, int Cin, int cout);
+size_t tc_upconv_split_bytes(int B, int H, int W, int Cin);
+size_t tc_upconv_t_bytes(int B, int H, int W, int cout);
+int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, int Cin, int cout,
+                           const void* packed_bf16, void* split_scratch, float* t_out, cudaStream_t stream);
 // exact-fp32 implicit GEMM on the CUDA cores (modconv.cu); needs Cin % 16 == 0 and N % 4 == 0
 int conv_gemm_ffma_launch(const ConvGemmArgs& a, int taps, cudaStream_t stream);
 size_t tc_conv_planar_elems(int B, int H, int W, int C);  // elements of one planar operand half

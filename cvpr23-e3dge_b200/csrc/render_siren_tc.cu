@@ -63,6 +63,7 @@ struct SmemTC {
   float ray_o[3][TCM], ray_d[3][TCM];
   uint64_t full[TC_RING], empty[TC_RING];
   uint64_t a_ready[4], d_ready;
+  uint64_t a_half;  // EPI bit 1: channels [0,32) of block 0 are published (the next layer's first MMAs start)
   uint32_t tmem_slot;
 };
 static_assert(sizeof(SmemTC) + 1024 <= 227 * 1024, "shared memory budget");
@@ -162,12 +163,15 @@ __device__ __forceinline__ void store_a8_v(SmemTC& sm, int m, int n0, const floa
 // even predicated off, the per-element address arithmetic would cost the inference build ~3
 // instruction slots per element).
 // EPI: epilogue code variant of the hidden layers (bit 0: packed f32x2 FiLM / range reduction / split
-// and the FiLM rows fetched while the tcgen05.ld is in flight).
+// and the FiLM rows fetched while the tcgen05.ld is in flight; bit 1: every warp takes 8 channels of
+// each 32-channel half of a block instead of 16 contiguous ones, and the first half of block 0 is
+// published on its own barrier so that the next layer's MMAs start half a block earlier).
 template <int MODE, int CL, bool STASH, int EPI>
 // 18 warps: one scheduler holds 5 of them, so 16384 / (5 * 32) = 102 -> 96 registers per thread
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ CUtensorMap wmap,
                        const int use_wmap) {
+  static_assert(EPI == 0 || EPI == 1 || EPI == 3, "the half-block column mapping needs the packed epilogue");
   extern __shared__ uint8_t smem_raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -181,6 +185,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
     for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], TC_COMPUTE_WARPS);
     mbar_init(&sm.d_ready, 1);
+    mbar_init(&sm.a_half, TC_COMPUTE_WARPS);
     fence_mbar_init();
   }
   for (int i = tid; i < SW; i += TC_NTHREADS) sm.wsig[i] = a.packed[OFF_WSIG + i];
@@ -238,7 +243,9 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         for (int l = 0; l < gemm_layers; ++l) {  // l-th GEMM of the tile = reference layer l+1
           const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256;
           for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&sm.a_ready[kb], pa);  // k-block kb of this layer's A operand is published
+            // k-block kb of this layer's A operand is published
+            if ((EPI & 2) && kb == 0) mbar_wait(&sm.a_half, pa);
+            else mbar_wait(&sm.a_ready[kb], pa);
             if (tr) a.trace[128 + l * 8 + kb] = clock64();
             tc::fence_after_thread_sync();
             const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
@@ -257,6 +264,10 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
+                if ((EPI & 2) && kb == 0 && pr == 0 && ks == 2) {  // second half of block 0
+                  mbar_wait(&sm.a_ready[0], pa);
+                  tc::fence_after_thread_sync();
+                }
                 const uint64_t bk = tc::advance_desc_k(dB, ks);
                 if (pr == 0) {
                   tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
@@ -306,6 +317,15 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.a_ready[j]);
     };
+
+    auto publish_half = [&]() {
+      fence_proxy_async();
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.a_half);
+    };
+    // first channel of this warp's g8-th group of 8 inside a 64-channel block
+    auto col_of = [&](int g8) -> int { return (EPI & 2) ? g8 * 32 + hw * 8 : hw * 16 + g8 * 8; };
 
     for (int slot = 0; slot < n_my_tiles; ++slot) {
       const int tile_raw = blockIdx.x + slot * gridDim.x;
@@ -416,7 +436,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
-          const int n0 = j * 64 + hw * 16 + g8 * 8;
+          const int n0 = j * 64 + col_of(g8);
           float v[8];
 #pragma unroll
           for (int i4 = 0; i4 < 2; ++i4) {
@@ -435,6 +455,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           }
           store_a8(sm, m, n0, v);
           if (taps) store_tap(0, n0, v);
+          if ((EPI & 2) && j == 0 && g8 == 0) publish_half();
         }
         publish(j);
         if (tr) a.trace[1 + j] = clock64();
@@ -448,6 +469,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         if (tr) a.trace[l * 8] = clock64();
         tc::fence_after_thread_sync();
         const uint32_t dsrc = trow + (uint32_t)((l - 1) & 1) * 256;  // GEMM index l-1 -> TMEM half
+        const uint32_t dsrc0 = dsrc - hw * 16;                       // column 0 of that accumulator
         const bool last = (l == 7);
         const bool feed = !last || a.with_view;
         const float* la = nullptr;
@@ -462,11 +484,14 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           float4 fg[4], fb[4];
           if (EPI & 1) {
             uint32_t accr[16];
-            tc::tmem_ld_32x16_issue(dsrc + j * 64, accr);
-            const float4* gp = reinterpret_cast<const float4*>(&sm.film[l][0][j * 64 + hw * 16]);
-            const float4* bp = reinterpret_cast<const float4*>(&sm.film[l][1][j * 64 + hw * 16]);
+            if (EPI & 2) tc::tmem_ld_2x32x8_issue(dsrc0 + j * 64 + hw * 8, accr);
+            else tc::tmem_ld_32x16_issue(dsrc + j * 64, accr);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) fg[i] = gp[i], fb[i] = bp[i];
+            for (int i = 0; i < 4; ++i) {
+              const int n = j * 64 + col_of(i >> 1) + (i & 1) * 4;
+              fg[i] = *reinterpret_cast<const float4*>(&sm.film[l][0][n]);
+              fb[i] = *reinterpret_cast<const float4*>(&sm.film[l][1][n]);
+            }
             tc::tmem_ld_wait16(accr);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(accr[i]);
@@ -476,7 +501,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           if (tr && l == 3) a.trace[384 + j * 8] = clock64();
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
-            const int n0 = j * 64 + hw * 16 + g8 * 8;
+            const int n0 = j * 64 + col_of(g8);
             float v[8];
             if (EPI & 1) {
 #pragma unroll
@@ -515,6 +540,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             }
             if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
             if (feed) store_a8_v<EPI>(sm, m, n0, v);
+            if ((EPI & 2) && feed && j == 0 && g8 == 0) publish_half();
             if (tr && l == 3) a.trace[384 + j * 8 + 2 + g8 * 2] = clock64();
           }
           if (feed) publish(j);
@@ -770,7 +796,8 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
     const char* e = getenv("E3DGE_RENDER_EPI");  // measurement aid: epilogue code variant
     epi = e ? atoi(e) : 0;
   }
-  if (mode == 0 && cl == 1 && epi == 1) return launch_tc_variant<0, 1, false, 1>(a, stream);
+  if (mode == 0 && cl == 1 && !a.stash && epi == 1) return launch_tc_variant<0, 1, false, 1>(a, stream);
+  if (mode == 0 && cl == 1 && !a.stash && epi == 3) return launch_tc_variant<0, 1, false, 3>(a, stream);
   if (mode == 0) {
     if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
     if (cl == 2) return launch_tc_variant<0, 2>(a, stream);

@@ -80,9 +80,14 @@ __global__ void __launch_bounds__(256) modulate_split_kernel(const float* __rest
 }
 
 // K-major bf16 hi/lo weights:  plain    Wk[o][tap*cin + ci]        = scale * W[o][ci][tap]
-//                              upsample Wk[tap*cout + o][ci]        = scale * W[o][ci][tap]
+//                              upsample Wk[o][tq*cin + ci]         = scale * W[o][ci][kUpTapOrder[tq]]
+//                                       (taps grouped by output parity phase, see tc_upconv_phase_kernel)
 // backward (input gradients):  mode 2   Wk[ci][tap*cout + o]       = scale * W[o][ci][8 - tap]  (plain conv)
 //                              mode 3   Wk[ci][tap*cout + o]       = scale * W[o][ci][tap]      (up-conv, planar gather)
+// conv taps (ky*3 + kx) in parity-phase order: phase (py,px) = (0,0): taps with even ky and kx (4),
+// (0,1): even ky, kx = 1 (2), (1,0): ky = 1, even kx (2), (1,1): the centre tap
+__constant__ int kUpTapOrder[9] = {0, 2, 6, 8, 1, 7, 3, 5, 4};
+
 __global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int cin, int upsample,
                                       float scale, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo) {
@@ -97,10 +102,10 @@ __global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int
       tap = k / cout;
       if (upsample == 2) tap = 8 - tap;
     } else if (upsample) {
-      ci = (int)(idx % cin);
-      const int n = (int)(idx / cin);
-      o = n % cout;
-      tap = n / cout;
+      const int k = (int)(idx % ((int64_t)9 * cin));
+      o = (int)(idx / ((int64_t)9 * cin));
+      ci = k % cin;
+      tap = kUpTapOrder[k / cin];
     } else {
       const int k = (int)(idx % ((int64_t)9 * cin));
       o = (int)(idx / ((int64_t)9 * cin));
@@ -290,6 +295,275 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) tc::tmem_dealloc(tmem_base, TC_ACC_BUFS * TC_BN);
 }
 
+// ---- upsampling conv on the tensor cores: parity-phase formulation ------------------------------
+// conv_transpose2d(stride 2, 3x3) output T[P,Q] (P in [0,2H], Q in [0,2W]) splits by the parity of
+// (P,Q) into four dense convolutions of the INPUT grid with 4 / 2 / 2 / 1 taps:
+//   T[2i+py, 2j+px] = sum_{ky = py (mod 2), kx = px (mod 2)} xs[i - (ky>>1), j - (kx>>1)] * W[ky,kx]
+// — the same 9*Cin*Cout MACs per input pixel as the G = xs*W GEMM, but the taps accumulate in TMEM, so
+// what reaches HBM is T (4 values per input pixel and channel) instead of G (9), and the consumer is a
+// plain 4x4 blur stencil instead of a 49-vector gather.
+// Activations are laid out with one zero column after every row and one zero row after every image
+// ([B][H+1][W+1][Cin]): a tap shift is then a 1-D shift of the flat pixel index m (the pad supplies the
+// zero neighbour across row / image borders, TMA zero-fills m < 0 and m >= Mp), the even phases' extra
+// row i = H / column j = W falls out of the same grid, and the tile is just 128 consecutive m.
+struct UpPhaseArgs {
+  float* t_out;  // [4 phases][Mp][N]
+  int Mp, N, Cin, Wp;
+};
+
+__global__ void __launch_bounds__(256) modulate_split_padded_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ s,
+                                                                    __nv_bfloat16* __restrict__ hi,
+                                                                    __nv_bfloat16* __restrict__ lo,
+                                                                    int64_t n_vec8, int H, int W, int cin) {
+  const int c8n = cin >> 3;
+  const int Wp = W + 1, Hp = H + 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8n) * 8;
+    const int64_t pp = i / c8n;  // padded pixel index
+    const int jx = (int)(pp % Wp), iy = (int)((pp / Wp) % Hp), b = (int)(pp / ((int64_t)Wp * Hp));
+    uint4 h4 = make_uint4(0, 0, 0, 0), l4 = h4;
+    if (jx < W && iy < H) {
+      const int64_t pix = ((int64_t)b * H + iy) * W + jx;
+      const float4 v0 = *reinterpret_cast<const float4*>(x + pix * cin + c);
+      const float4 v1 = *reinterpret_cast<const float4*>(x + pix * cin + c + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(s + (size_t)b * cin + c);
+      const float4 s1 = *reinterpret_cast<const float4*>(s + (size_t)b * cin + c + 4);
+      const float v[8] = {v0.x * s0.x, v0.y * s0.y, v0.z * s0.z, v0.w * s0.w,
+                          v1.x * s1.x, v1.y * s1.y, v1.z * s1.z, v1.w * s1.w};
+      __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc::split_bf16(v[j], h[j], l[j]);
+      h4 = *reinterpret_cast<const uint4*>(h);
+      l4 = *reinterpret_cast<const uint4*>(l);
+    }
+    *reinterpret_cast<uint4*>(hi + pp * cin + c) = h4;
+    *reinterpret_cast<uint4*>(lo + pp * cin + c) = l4;
+  }
+}
+
+// Same pipeline as tc_conv_kernel (TMA producer warp, single-thread MMA issuer, 8 epilogue warps,
+// 3-stage ring, ping-pong TMEM accumulators); a tile = (128 consecutive padded pixels) x (128 output
+// channels) x (one parity phase).  Phases cost 4:2:2:1, so the phase of a tile is rotated by the
+// CTA's round number (gridDim.x is a multiple of 4 * n-tiles): every CTA walks all four phases.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                       const __grid_constant__ UpPhaseArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* acc_full = empty + TC_STAGES;
+  uint64_t* acc_empty = acc_full + TC_ACC_BUFS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_BUFS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = a.N / TC_BN;
+  const int m_tiles = (a.Mp + TC_BM - 1) / TC_BM;
+  const int n_tiles = 4 * m_tiles * n_tiles_n;
+  const int kpt = a.Cin / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&tmA_hi);
+    tc::prefetch_tensormap(&tmA_lo);
+    tc::prefetch_tensormap(&tmB_hi);
+    tc::prefetch_tensormap(&tmB_lo);
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < TC_ACC_BUFS; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], TC_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TC_ACC_BUFS * TC_BN);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (phase, first padded pixel, first channel); n fastest, then the phase slot, then m
+  auto tile_coords = [&](int tile, int& phase, int& m0, int& n0) {
+    const int nt = tile % n_tiles_n, rest = tile / n_tiles_n;
+    phase = ((rest & 3) + tile / (int)gridDim.x) & 3;
+    m0 = (rest >> 2) * TC_BM;
+    n0 = nt * TC_BN;
+  };
+  // phase p = py*2 + px: number of taps, first tap slot of the packed K axis
+  auto phase_taps = [](int p, int& ntaps, int& tq0) {
+    ntaps = p == 0 ? 4 : (p == 3 ? 1 : 2);
+    tq0 = p == 0 ? 0 : (p == 1 ? 4 : (p == 2 ? 6 : 8));
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase_bit = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int p, m0, n0, ntaps, tq0;
+        tile_coords(tile, p, m0, n0);
+        phase_taps(p, ntaps, tq0);
+        for (int t = 0; t < ntaps; ++t) {
+          // flat shift of tap t: (ky>>1) rows and (kx>>1) columns back
+          int shift;
+          if (p == 0) shift = (t >> 1) * a.Wp + (t & 1);
+          else if (p == 1) shift = t * a.Wp;
+          else shift = t;  // p == 2: kx = 0, 2;  p == 3: the centre tap
+          for (int kc = 0; kc < kpt; ++kc) {
+            mbar_wait(&empty[stage], phase_bit ^ 1);
+            mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+            uint8_t* st = smem + stage * TC_STAGE_BYTES;
+            tc::tma_load_2d(st, &tmA_hi, &full[stage], kc * TC_BK, m0 - shift);
+            tc::tma_load_2d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, m0 - shift);
+            tc::tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[stage], (tq0 + t) * a.Cin + kc * TC_BK, n0);
+            tc::tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[stage], (tq0 + t) * a.Cin + kc * TC_BK, n0);
+            if (++stage == TC_STAGES) {
+              stage = 0;
+              phase_bit ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, TC_BN);
+      uint32_t stage = 0, phase_bit = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        int p, m0, n0, ntaps, tq0;
+        tile_coords(tile, p, m0, n0);
+        phase_taps(p, ntaps, tq0);
+        const int nkb = ntaps * kpt;
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+        tc::fence_after_thread_sync();
+        const uint32_t dcol = tmem_base + buf * TC_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase_bit);
+          tc::fence_after_thread_sync();
+          const uint32_t sb = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint64_t dA_hi = tc::make_smem_desc_sw128(sb);
+          const uint64_t dA_lo = tc::make_smem_desc_sw128(sb + TC_TILE_BYTES);
+          const uint64_t dB_hi = tc::make_smem_desc_sw128(sb + 2 * TC_TILE_BYTES);
+          const uint64_t dB_lo = tc::make_smem_desc_sw128(sb + 3 * TC_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 16; ++ks) {
+            const uint64_t ah = tc::advance_desc_k(dA_hi, ks), al = tc::advance_desc_k(dA_lo, ks);
+            const uint64_t bh = tc::advance_desc_k(dB_hi, ks), bl = tc::advance_desc_k(dB_lo, ks);
+            tc::mma_bf16_ss(dcol, ah, bh, idesc, (kb | ks) != 0);
+            tc::mma_bf16_ss(dcol, ah, bl, idesc, true);
+            tc::mma_bf16_ss(dcol, al, bh, idesc, true);
+          }
+          tc::mma_commit(&empty[stage]);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase_bit ^= 1;
+          }
+        }
+        tc::mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      int p, m0, n0;
+      tile_coords(tile, p, m0, n0);
+      const uint32_t buf = it & 1, use = it >> 1;
+      const int m = m0 + row;
+      const bool valid = m < a.Mp;
+      float* orow = a.t_out + ((size_t)p * a.Mp + (valid ? m : 0)) * a.N + n0;
+      mbar_wait(&acc_full[buf], use & 1);
+      tc::fence_after_thread_sync();
+      constexpr int kChunksPerWarp = TC_BN / 32 / (TC_EPI_WARPS / 4);
+#pragma unroll 1
+      for (int chunk = chalf * kChunksPerWarp; chunk < (chalf + 1) * kChunksPerWarp; ++chunk) {
+        float v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
+        if (chunk == (chalf + 1) * kChunksPerWarp - 1) {
+          tc::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (!valid) continue;
+        float4* dst = reinterpret_cast<float4*>(orow + chunk * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TC_ACC_BUFS * TC_BN);
+}
+
+bool tc_upconv_supported(int B, int H, int W, int Cin, int cout) {
+  return B > 0 && H > 0 && W > 0 && Cin % TC_BK == 0 && cout % TC_BN == 0 &&
+         (int64_t)B * (H + 1) * (W + 1) < (1ll << 30);
+}
+size_t tc_upconv_split_bytes(int B, int H, int W, int Cin) {
+  return (size_t)B * (H + 1) * (W + 1) * Cin * 2 * sizeof(__nv_bfloat16);
+}
+size_t tc_upconv_t_bytes(int B, int H, int W, int cout) {
+  return (size_t)4 * B * (H + 1) * (W + 1) * cout * sizeof(float);
+}
+
+// x [B,H,W,Cin] fp32 NHWC, s [B,Cin] -> t_out [4][B*(H+1)*(W+1)][cout]; split_scratch holds the padded
+// bf16 hi / lo operand halves (tc_upconv_split_bytes).
+int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, int Cin, int cout,
+                           const void* packed_bf16, void* split_scratch, float* t_out, cudaStream_t stream) {
+  E3_REQUIRE(tc_upconv_supported(B, H, W, Cin, cout), E3_ERR_UNSUPPORTED,
+             "tensor-core up-conv: unsupported shape B=%d H=%d W=%d Cin=%d cout=%d (needs Cin %% 64 == 0, "
+             "cout %% 128 == 0)", B, H, W, Cin, cout);
+  const int64_t Mp = (int64_t)B * (H + 1) * (W + 1);
+  __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
+  __nv_bfloat16* xs_lo = xs_hi + Mp * Cin;
+  {
+    const int64_t nv = Mp * Cin / 8;
+    int blocks = (int)((nv + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    modulate_split_padded_kernel<<<blocks, 256, 0, stream>>>(x, s, xs_hi, xs_lo, nv, H, W, Cin);
+    E3_CUDA(cudaGetLastError());
+  }
+  const int K = 9 * Cin;
+  const __nv_bfloat16* w_hi = static_cast<const __nv_bfloat16*>(packed_bf16);
+  const __nv_bfloat16* w_lo = w_hi + (size_t)cout * K;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  const uint64_t adims[2] = {(uint64_t)Cin, (uint64_t)Mp};
+  const uint64_t astr[1] = {(uint64_t)Cin * 2};
+  const uint32_t abox[2] = {(uint32_t)TC_BK, (uint32_t)TC_BM};
+  const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)cout};
+  const uint64_t bstr[1] = {(uint64_t)K * 2};
+  const uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)TC_BN};
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA_hi, xs_hi, 2, adims, astr, abox))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmA_lo, xs_lo, 2, adims, astr, abox))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox))) return rc;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    E3_CUDA(cudaFuncSetAttribute((const void*)tc_upconv_phase_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  UpPhaseArgs a{t_out, (int)Mp, cout, Cin, W + 1};
+  const int group = 4 * (cout / TC_BN);  // tiles that share one m-tile: all phases x n-tiles
+  const int n_tiles = group * (int)((Mp + TC_BM - 1) / TC_BM);
+  int grid = sm_count() / group * group;  // multiple of the group: the phase rotation stays a bijection
+  if (grid < group) grid = group;
+  if (grid > n_tiles) grid = n_tiles;
+  tc_upconv_phase_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
 bool tc_conv_supported(int B, int H, int W, int Cin, int N) {
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   return B > 0 && pow2(W) && pow2(H) && W >= 8 && H * W >= 64 && Cin % TC_BK == 0 && N % TC_BN == 0;
@@ -322,35 +596,14 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
   const size_t n_act = (size_t)a.B * a.H * a.W * a.Cin;
   __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
   __nv_bfloat16* xs_lo = xs_hi + n_act;
-  int rc = tc_conv_split(a, split_scratch, stream);
-  if (rc) return rc;
+  {
+    const int64_t nv = (int64_t)(n_act / 8);
+    int blocks = (int)((nv + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    modulate_split_kernel<<<blocks, 256, 0, stream>>>(a.x, a.s, xs_hi, xs_lo, nv, a.H * a.W, a.Cin);
+    E3_CUDA(cudaGetLastError());
+  }
   return tc_conv_launch_presplit(a, taps, packed_bf16, xs_hi, xs_lo, stream);
-}
-
-int tc_conv_split(const ConvGemmArgs& a, void* split_scratch, cudaStream_t stream) {
-  const size_t n_act = (size_t)a.B * a.H * a.W * a.Cin;
-  __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
-  __nv_bfloat16* xs_lo = xs_hi + n_act;
-  const int64_t nv = (int64_t)(n_act / 8);
-  int blocks = (int)((nv + 255) / 256);
-  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-  modulate_split_kernel<<<blocks, 256, 0, stream>>>(a.x, a.s, xs_hi, xs_lo, nv, a.H * a.W, a.Cin);
-  E3_CUDA(cudaGetLastError());
-  return E3_OK;
-}
-
-static int tc_conv_launch_checked(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
-                                  const void* xs_lo, cudaStream_t stream);
-
-// Plain GEMM G[m][n] = sum_ci xs[m][ci] * Wk[n][ci] over a run of m_rows pixels (a multiple of 128):
-// the 1-tap kernel on the run viewed as one image of m_rows/128 rows x 128 pixels.
-int tc_gemm_rows_presplit(const void* xs_hi, const void* xs_lo, int64_t m_rows, int Cin, int N,
-                          const void* packed_bf16, float* out, cudaStream_t stream) {
-  E3_REQUIRE(m_rows > 0 && m_rows % TC_BM == 0 && m_rows / TC_BM < (1 << 24) && Cin % TC_BK == 0 && N % TC_BN == 0,
-             E3_ERR_UNSUPPORTED, "tensor-core GEMM: unsupported shape M=%lld Cin=%d N=%d", (long long)m_rows, Cin, N);
-  ConvGemmArgs a{};
-  a.out = out, a.B = 1, a.H = (int)(m_rows / TC_BM), a.W = TC_BM, a.Cin = Cin, a.N = N, a.mode = 0;
-  return tc_conv_launch_checked(a, 1, packed_bf16, xs_hi, xs_lo, stream);
 }
 
 int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
@@ -359,11 +612,6 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
              "tensor-core conv: unsupported shape B=%d H=%d W=%d Cin=%d N=%d (needs power-of-two "
              "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0)", a.B, a.H, a.W, a.Cin, a.N);
   E3_REQUIRE(!a.planar || taps == 9, E3_ERR_BAD_ARG, "tensor-core conv: planar operands need 9 taps");
-  return tc_conv_launch_checked(a, taps, packed_bf16, xs_hi, xs_lo, stream);
-}
-
-static int tc_conv_launch_checked(const ConvGemmArgs& a, int taps, const void* packed_bf16, const void* xs_hi,
-                                  const void* xs_lo, cudaStream_t stream) {
   TcTile t;
   t.bw = a.W < 128 ? a.W : 128;
   t.bh = (128 / t.bw) < a.H ? (128 / t.bw) : a.H;

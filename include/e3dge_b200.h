@@ -259,7 +259,7 @@ int e3_nhwc_to_nchw(const float* x, float* y, int batch, int ch, int h, int w, v
  * `decoder.*.conv.weight` without its leading 1): the equalised-lr scale 1/sqrt(cin*9)
  * (stylesdf_model.py:301-302) is folded in and the taps are laid out GEMM-major
  * (plain: [tap][cin][cout]; upsample: [cin][tap*cout]), followed by the K-major bf16 hi/lo
- * split the tensor-core path reads through TMA.  Pack once per weight update. */
+ * split the tensor-core path reads through TMA (upsample: taps ordered by output parity phase).  Pack once per weight update. */
 size_t e3_conv_packed_bytes(int cout, int cin);
 int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample, void* packed,
                         void* stream);
@@ -268,9 +268,8 @@ int e3_conv_pack_weight(const float* weight, int cout, int cin, int upsample, vo
 #define E3_CONV_AUTO 0u            /* tensor cores when the shape allows, else CUDA cores */
 #define E3_CONV_FP32_CUDA_CORES 1u /* exact-fp32 FFMA implicit GEMM */
 #define E3_CONV_TENSOR_CORES 2u    /* tcgen05 split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate in
-                                      TMEM); E3_ERR_UNSUPPORTED unless H, W are powers of two >= 8,
-                                      cin % 64 == 0 and the GEMM N (cout, or 9*cout when upsampling)
-                                      % 128 == 0 */
+                                      TMEM); E3_ERR_UNSUPPORTED unless cin % 64 == 0, cout % 128 == 0
+                                      and (plain conv only) H, W are powers of two >= 8 */
 
 /* StyledConv forward, plain 3x3 (stylesdf_model.py:356-360, 494-507):
  *   y = lrelu_0.2( d[b,o] * conv3x3(x * s[b,:], W/sqrt(cin*9)) + noise_w*noise[y,x]

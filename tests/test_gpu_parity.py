@@ -297,33 +297,6 @@ def test_tensor_core_conv_vs_fp32_path_and_oracle(cin, cout, hw, batch, up):
         assert rel_linf(y_tc.cpu(), y_ref) < 1e-4
 
 
-@pytest.mark.parametrize("cin,cout,hw,batch,band_kb", [
-    (64, 128, 32, 3, 600),     # 4-row bands (one GEMM tile = 4 rows), halo rows both sides, 8 bands per image
-    (64, 128, 32, 3, 4800),    # whole-image bands (band >= one image, < batch)
-    (128, 128, 128, 2, 9000),  # 128-wide rows, 14-row bands that straddle the image boundary
-])
-def test_banded_upconv_is_bit_identical_to_the_single_pass(cin, cout, hw, batch, band_kb, monkeypatch):
-    """e3_styled_conv3x3_up_fwd runs GEMM + col2im band by band so that G stays in L2; the bands (with
-    their halo rows) must reproduce the one-pass result exactly."""
-    from e3dge_b200.stylesdf_model import StyledConv
-    g = np.random.Generator(np.random.PCG64(cin + cout + hw + batch + band_kb))
-    f32 = lambda *s: torch.from_numpy(g.standard_normal(s).astype(np.float32))
-    m = StyledConv(cin, cout, 3, 512, upsample=True)
-    sd = {"conv.weight": f32(1, cout, cin, 3, 3), "conv.modulation.weight": f32(cin, 512),
-          "conv.modulation.bias": 1 + 0.1 * f32(cin), "noise.weight": 0.1 * f32(1),
-          "activate.bias": 0.1 * f32(cout), "bias": torch.zeros(1, cout, 1, 1)}
-    m.load_state_dict(sd, strict=False)
-    m = m.cuda()
-    _set_backend(m, "tensor_cores")
-    x, lat, noise = f32(batch, cin, hw, hw).cuda(), f32(batch, 512).cuda(), f32(1, 1, 2 * hw, 2 * hw).cuda()
-    with torch.no_grad():
-        monkeypatch.setenv("E3DGE_UPCONV_BAND_KB", "0")
-        y_one = m(x, lat, noise=noise)
-        monkeypatch.setenv("E3DGE_UPCONV_BAND_KB", str(band_kb))
-        y_band = m(x, lat, noise=noise)
-    assert torch.equal(y_one, y_band)
-
-
 def test_tensor_core_request_on_unsupported_shape_fails_loudly():
     from e3dge_b200.stylesdf_model import StyledConv
     m = StyledConv(16, 24, 3, 512).cuda()
