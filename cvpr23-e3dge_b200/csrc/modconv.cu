@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(256) col2im_blur_act_kernel(const __grid_const
 // T[P,Q] (P in [0,2H], Q in [0,2W]) lives as four phase planes on the padded grid (tc_conv.cu):
 //   T[2i+py, 2j+px, o] = t[(py*2+px)][(b*(H+1) + i)*(W+1) + j][o]
 // out[Y,X,o] = lrelu( d * sum_{a,c<4} kb[a] kb[c] T[Y+a-1, X+c-1, o] + noise + bias ) * sqrt2, kb = [1,3,3,1]/4.
-// One thread = a 2x2 output block x 4 channels: T rows 2y-1 .. 2y+3 = (odd,y-1) (even,y) (odd,y) (even,y+1)
-// (odd,y+1), same along x: 25 vector reads for 16 outputs.
+// One thread = 2x2 input pixels = a 4x4 output block x 4 channels: T rows 2y-1 .. 2y+5 = (odd,y-1) (even,y)
+// (odd,y) (even,y+1) (odd,y+1) (even,y+2) (odd,y+2), same along x: 49 vector reads for 64 outputs.
 struct UpBlurArgs {
   const float* t;  // [4][Mp][cout]
   float* y;        // [B,2H,2W,cout]
@@ -355,60 +355,67 @@ struct UpBlurArgs {
   const float* act_bias;  // NULL: bare modulated conv
 };
 
+// weight of T row r (0..6, relative to 2y-1) in output row 2y+k (k = 0..3): kb[r - k], kb = [1,3,3,1]/4
+__device__ __forceinline__ float blur_w(int r, int k) {
+  const int i = r - k;
+  return (i == 0 || i == 3) ? .25f : ((i == 1 || i == 2) ? .75f : 0.f);
+}
+
 __global__ void __launch_bounds__(256) upconv_blur_act_kernel(const __grid_constant__ UpBlurArgs a) {
   const int c4n = a.cout >> 2;
   const int OW = 2 * a.W, OH = 2 * a.H, Wp = a.W + 1, Hp = a.H + 1;
+  const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1;
   const int64_t Mp = (int64_t)a.B * Hp * Wp;
-  const int64_t total = (int64_t)a.B * a.H * a.W * c4n;
+  const int64_t total = (int64_t)a.B * H2 * W2 * c4n;
   const bool linear = a.act_bias == nullptr;
   const float nw = linear ? 0.f : a.noise_w[0];
-  const float w0[5] = {.25f, .75f, .75f, .25f, 0.f};  // weight of T row r (of 5) in output row 2y
-  const float w1[5] = {0.f, .25f, .75f, .75f, .25f};  // ... in output row 2y+1
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int o = (int)(idx % c4n) * 4;
     int64_t t = idx / c4n;
-    const int x = (int)(t % a.W);
-    t /= a.W;
-    const int y = (int)(t % a.H);
-    const int b = (int)(t / a.H);
-    float4 acc[2][2];
+    const int x = (int)(t % W2) * 2;
+    t /= W2;
+    const int y = (int)(t % H2) * 2;
+    const int b = (int)(t / H2);
+    float4 acc[4][4];
 #pragma unroll
-    for (int py = 0; py < 2; ++py)
+    for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
-      for (int px = 0; px < 2; ++px) acc[py][px] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kx = 0; kx < 4; ++kx) acc[ky][kx] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      const int pr = (r & 1) ^ 1;           // rows alternate odd, even, odd, even, odd
-      const int i = y + ((r + 1) >> 1) - 1;  // y-1, y, y, y+1, y+1
+    for (int r = 0; r < 7; ++r) {
+      const int pr = (r & 1) ^ 1;            // rows alternate odd, even, odd, ...
+      const int i = y + ((r + 1) >> 1) - 1;  // y-1, y, y, y+1, y+1, y+2, y+2
       if (i < 0 || i >= a.H + (pr ? 0 : 1)) continue;
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
+      for (int c = 0; c < 7; ++c) {
         const int pc = (c & 1) ^ 1;
         const int j = x + ((c + 1) >> 1) - 1;
         if (j < 0 || j >= a.W + (pc ? 0 : 1)) continue;
         const float4 tv = *reinterpret_cast<const float4*>(
             a.t + ((size_t)(pr * 2 + pc) * Mp + ((size_t)b * Hp + i) * Wp + j) * a.cout + o);
-        const float k00 = w0[r] * w0[c], k01 = w0[r] * w1[c], k10 = w1[r] * w0[c], k11 = w1[r] * w1[c];
-        if (k00 != 0.f) acc[0][0].x = fmaf(k00, tv.x, acc[0][0].x), acc[0][0].y = fmaf(k00, tv.y, acc[0][0].y),
-                        acc[0][0].z = fmaf(k00, tv.z, acc[0][0].z), acc[0][0].w = fmaf(k00, tv.w, acc[0][0].w);
-        if (k01 != 0.f) acc[0][1].x = fmaf(k01, tv.x, acc[0][1].x), acc[0][1].y = fmaf(k01, tv.y, acc[0][1].y),
-                        acc[0][1].z = fmaf(k01, tv.z, acc[0][1].z), acc[0][1].w = fmaf(k01, tv.w, acc[0][1].w);
-        if (k10 != 0.f) acc[1][0].x = fmaf(k10, tv.x, acc[1][0].x), acc[1][0].y = fmaf(k10, tv.y, acc[1][0].y),
-                        acc[1][0].z = fmaf(k10, tv.z, acc[1][0].z), acc[1][0].w = fmaf(k10, tv.w, acc[1][0].w);
-        if (k11 != 0.f) acc[1][1].x = fmaf(k11, tv.x, acc[1][1].x), acc[1][1].y = fmaf(k11, tv.y, acc[1][1].y),
-                        acc[1][1].z = fmaf(k11, tv.z, acc[1][1].z), acc[1][1].w = fmaf(k11, tv.w, acc[1][1].w);
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) {
+            const float k = blur_w(r, ky) * blur_w(c, kx);
+            if (k != 0.f) {
+              acc[ky][kx].x = fmaf(k, tv.x, acc[ky][kx].x), acc[ky][kx].y = fmaf(k, tv.y, acc[ky][kx].y);
+              acc[ky][kx].z = fmaf(k, tv.z, acc[ky][kx].z), acc[ky][kx].w = fmaf(k, tv.w, acc[ky][kx].w);
+            }
+          }
       }
     }
     const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);
     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!linear) bv = *reinterpret_cast<const float4*>(a.act_bias + o);
 #pragma unroll
-    for (int py = 0; py < 2; ++py)
+    for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        const int Y = 2 * y + py, X = 2 * x + px;
-        const float4 s4 = acc[py][px];
+      for (int kx = 0; kx < 4; ++kx) {
+        const int Y = 2 * y + ky, X = 2 * x + kx;
+        if (Y >= OH || X >= OW) continue;  // odd H / W: the last block is half empty
+        const float4 s4 = acc[ky][kx];
         float v[4] = {s4.x * dv.x, s4.y * dv.y, s4.z * dv.z, s4.w * dv.w};
         if (!linear) {
           const float nz = nw * a.noise[(size_t)b * a.noise_bstride + (size_t)Y * OW + X];
@@ -690,7 +697,7 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
     UpBlurArgs u{};
     u.t = t_out, u.y = y, u.B = batch, u.H = h, u.W = w, u.cout = cout;
     u.d = d, u.noise = noise, u.noise_bstride = noise_batch_stride, u.noise_w = noise_w, u.act_bias = act_bias;
-    const int64_t total = (int64_t)batch * h * w * (cout / 4);
+    const int64_t total = (int64_t)batch * ((h + 1) / 2) * ((w + 1) / 2) * (cout / 4);
     upconv_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(u);
     E3_CUDA(cudaGetLastError());
     return E3_OK;

@@ -165,13 +165,21 @@ __device__ __forceinline__ void store_a8_v(SmemTC& sm, int m, int n0, const floa
 // EPI: epilogue code variant of the hidden layers (bit 0: packed f32x2 FiLM / range reduction / split
 // and the FiLM rows fetched while the tcgen05.ld is in flight; bit 1: every warp takes 8 channels of
 // each 32-channel half of a block instead of 16 contiguous ones, and the first half of block 0 is
-// published on its own barrier so that the next layer's MMAs start half a block earlier).
+// published on its own barrier so that the next layer's MMAs start half a block earlier; bit 2: CTA
+// pairs — the two CTAs of a cluster (CL = 2) run their tiles in lockstep through ONE tcgen05.mma
+// cta_group::2 stream issued by the leader: M = 256 = 128 rows from each CTA, every CTA's ring holds one
+// N-half of each 256 x 64 weight block, so per SM the B-operand reads and the weight stream are halved
+// (shared-memory bandwidth is what paces the single-CTA MMAs) and the ring is twice as deep in blocks).
 template <int MODE, int CL, bool STASH, int EPI>
 // 18 warps: one scheduler holds 5 of them, so 16384 / (5 * 32) = 102 -> 96 registers per thread
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ CUtensorMap wmap,
                        const int use_wmap) {
-  static_assert(EPI == 0 || EPI == 1 || EPI == 3, "the half-block column mapping needs the packed epilogue");
+  static_assert(EPI == 0 || EPI == 1 || EPI == 3 || EPI == 7, "the half-block column mapping needs the packed epilogue");
+  constexpr bool PAIR = (EPI & 4) != 0;
+  static_assert(!PAIR || CL == 2, "CTA pairs are clusters of two");
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = pair_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   SmemTC& sm = *reinterpret_cast<SmemTC*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -180,16 +188,21 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
     for (int s = 0; s < TC_RING; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], CL);
+      mbar_init(&sm.empty[s], PAIR ? 1 : CL);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], TC_COMPUTE_WARPS);
+    for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], (PAIR ? 2 : 1) * TC_COMPUTE_WARPS);
     mbar_init(&sm.d_ready, 1);
-    mbar_init(&sm.a_half, TC_COMPUTE_WARPS);
+    mbar_init(&sm.a_half, (PAIR ? 2 : 1) * TC_COMPUTE_WARPS);
     fence_mbar_init();
   }
   for (int i = tid; i < SW; i += TC_NTHREADS) sm.wsig[i] = a.packed[OFF_WSIG + i];
-  if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 512);
+  if (PAIR) {
+    cluster_sync_all();  // both CTAs are resident and their barriers initialised before the paired alloc
+    if (warp == 1) tc::tmem_alloc_pair(&sm.tmem_slot, 512);
+  } else if (warp == 1) {
+    tc::tmem_alloc(&sm.tmem_slot, 512);
+  }
   tc::fence_before_thread_sync();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any multicast lands
@@ -209,6 +222,21 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       const int per_tile = gemm_layers * TC_TILES_PER_LAYER;
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
+        if (PAIR) {
+          // one stage = one 256(n) x 64(k) block over the pair: this CTA fetches its n-half, the bytes of
+          // both halves are counted on the leader's barrier
+          for (int c = 0; c < per_tile / 2; ++c) {
+            mbar_wait(&sm.empty[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * TC_TILE_BYTES);
+            tc::tma_load_2d_pair(sm.ring + stage * TC_TILE_BYTES, &wmap, tc::map_to_cta(&sm.full[stage], 0), 0,
+                                 (2 * c + (int)pair_rank) * 128);
+            if (++stage == TC_RING) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int c = 0; c < per_tile; ++c) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&sm.full[stage], TC_TILE_BYTES);
@@ -232,8 +260,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16_f32(128, 256);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = tc::make_idesc_bf16_f32(PAIR ? 256 : 128, 256);
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
       const bool skip_lo = (a.p.flags & DBG_SKIP_LO_MMA) != 0;
       const bool no_w = (a.p.flags & DBG_NO_WSTREAM) != 0;
@@ -244,8 +272,14 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256;
           for (int kb = 0; kb < 4; ++kb) {
             // k-block kb of this layer's A operand is published
-            if ((EPI & 2) && kb == 0) mbar_wait(&sm.a_half, pa);
-            else mbar_wait(&sm.a_ready[kb], pa);
+            if (PAIR) {
+              if ((EPI & 2) && kb == 0) tc::mbar_wait_cluster(&sm.a_half, pa);
+              else tc::mbar_wait_cluster(&sm.a_ready[kb], pa);
+            } else if ((EPI & 2) && kb == 0) {
+              mbar_wait(&sm.a_half, pa);
+            } else {
+              mbar_wait(&sm.a_ready[kb], pa);
+            }
             if (tr) a.trace[128 + l * 8 + kb] = clock64();
             tc::fence_after_thread_sync();
             const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
@@ -258,23 +292,37 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             for (int pr = 0; pr < 2; ++pr) {  // pr 0: W_hi block, pr 1: W_lo block
               if (!no_w) {
                 mbar_wait(&sm.full[stage], phase);
-                mbar_wait(&sm.full[stage + 1], phase);
+                if (!PAIR) mbar_wait(&sm.full[stage + 1], phase);
               }
               tc::fence_after_thread_sync();
               const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 if ((EPI & 2) && kb == 0 && pr == 0 && ks == 2) {  // second half of block 0
-                  mbar_wait(&sm.a_ready[0], pa);
+                  if (PAIR) tc::mbar_wait_cluster(&sm.a_ready[0], pa);
+                  else mbar_wait(&sm.a_ready[0], pa);
                   tc::fence_after_thread_sync();
                 }
                 const uint64_t bk = tc::advance_desc_k(dB, ks);
+                auto mma = [&](uint64_t da, bool accum) {
+                  if (PAIR) tc::mma_bf16_ss_pair(dcol, da, bk, idesc, accum);
+                  else tc::mma_bf16_ss(dcol, da, bk, idesc, accum);
+                };
                 if (pr == 0) {
-                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
-                  if (!skip_lo) tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+                  mma(tc::advance_desc_k(dAh, ks), (kb | ks) != 0);
+                  if (!skip_lo) mma(tc::advance_desc_k(dAl, ks), true);
                 } else if (!skip_lo) {
-                  tc::mma_bf16_ss(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, true);
+                  mma(tc::advance_desc_k(dAh, ks), true);
                 }
+              }
+              if (PAIR) {
+                if (!no_w) tc::mma_commit_pair(&sm.empty[stage], 3);
+                if (tr) a.trace[256 + l * 16 + kb * 4 + pr * 2 + 1] = clock64();
+                if (++stage == TC_RING) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+                continue;
               }
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -291,7 +339,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             }
           }
           pa ^= 1;  // each a_ready[kb] completes exactly once per layer
-          tc::mma_commit(&sm.d_ready);
+          if (PAIR) tc::mma_commit_pair(&sm.d_ready, 3);
+          else tc::mma_commit(&sm.d_ready);
         }
       }
     }
@@ -311,18 +360,32 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     const bool no_sin = (P.flags & DBG_NO_SIN) != 0;
 
     // publish k-block j of the next A operand: generic-proxy stores -> async proxy (UMMA)
+    // (pairs: the arrival goes to the leader CTA's barrier, release at cluster scope)
+    uint32_t ready_addr0 = 0, half_addr = 0;
+    if (PAIR) {
+      ready_addr0 = tc::map_to_cta(&sm.a_ready[0], 0);  // a_ready[j] sits 8*j bytes further on
+      half_addr = tc::map_to_cta(&sm.a_half, 0);
+    }
     auto publish = [&](int j) {
-      fence_proxy_async();
+      if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
+      else fence_proxy_async();
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.a_ready[j]);
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_cluster(ready_addr0 + 8u * (uint32_t)j);
+        else mbar_arrive(&sm.a_ready[j]);
+      }
     };
 
     auto publish_half = [&]() {
-      fence_proxy_async();
+      if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
+      else fence_proxy_async();
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.a_half);
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_cluster(half_addr);
+        else mbar_arrive(&sm.a_half);
+      }
     };
     // first channel of this warp's g8-th group of 8 inside a 64-channel block
     auto col_of = [&](int g8) -> int { return (EPI & 2) ? g8 * 32 + hw * 8 : hw * 16 + g8 * 8; };
@@ -722,7 +785,10 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
   tc::fence_before_thread_sync();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into its ring
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) {
+    if (PAIR) tc::tmem_dealloc_pair(tmem_base, 512);
+    else tc::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 template <int MODE, int CL, bool STASH = false, int EPI = 0>
@@ -794,10 +860,11 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   static int epi = -1;
   if (epi < 0) {
     const char* e = getenv("E3DGE_RENDER_EPI");  // measurement aid: epilogue code variant
-    epi = e ? atoi(e) : 0;
+    epi = e ? atoi(e) : 3;
   }
   if (mode == 0 && cl == 1 && !a.stash && epi == 1) return launch_tc_variant<0, 1, false, 1>(a, stream);
   if (mode == 0 && cl == 1 && !a.stash && epi == 3) return launch_tc_variant<0, 1, false, 3>(a, stream);
+  if (mode == 0 && !a.stash && epi == 7) return launch_tc_variant<0, 2, false, 7>(a, stream);
   if (mode == 0) {
     if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
     if (cl == 2) return launch_tc_variant<0, 2>(a, stream);
