@@ -191,9 +191,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       mbar_init(&sm.empty[s], PAIR ? 1 : CL);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], (PAIR ? 2 : 1) * TC_COMPUTE_WARPS);
+    // pairs: the leader's barriers also take one arrival per phase from the peer CTA's forwarder thread
+    const uint32_t n_arrive = TC_COMPUTE_WARPS + ((PAIR && leader) ? 1 : 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], n_arrive);
     mbar_init(&sm.d_ready, 1);
-    mbar_init(&sm.a_half, (PAIR ? 2 : 1) * TC_COMPUTE_WARPS);
+    mbar_init(&sm.a_half, n_arrive);
     fence_mbar_init();
   }
   for (int i = tid; i < SW; i += TC_NTHREADS) sm.wsig[i] = a.packed[OFF_WSIG + i];
@@ -260,6 +263,26 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    if (PAIR && !leader && lane == 0) {
+      // ===== peer CTA: forward "this CTA's epilogue warps have published" to the leader's barriers =====
+      // (the epilogue warps arrive locally — a remote release-arrive from each of them costs ~1k cycles
+      // on their critical path; here one otherwise idle thread pays it)
+      const uint32_t ready0 = tc::map_to_cta(&sm.a_ready[0], 0), half0 = tc::map_to_cta(&sm.a_half, 0);
+      uint32_t pa = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        for (int l = 0; l < gemm_layers; ++l) {
+          if (EPI & 2) {
+            mbar_wait(&sm.a_half, pa);
+            tc::mbar_arrive_cluster(half0);
+          }
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&sm.a_ready[kb], pa);
+            tc::mbar_arrive_cluster(ready0 + 8u * (uint32_t)kb);
+          }
+          pa ^= 1;
+        }
+      }
+    }
     if (lane == 0 && leader) {
       const uint32_t idesc = tc::make_idesc_bf16_f32(PAIR ? 256 : 128, 256);
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
@@ -360,32 +383,17 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     const bool no_sin = (P.flags & DBG_NO_SIN) != 0;
 
     // publish k-block j of the next A operand: generic-proxy stores -> async proxy (UMMA)
-    // (pairs: the arrival goes to the leader CTA's barrier, release at cluster scope)
-    uint32_t ready_addr0 = 0, half_addr = 0;
-    if (PAIR) {
-      ready_addr0 = tc::map_to_cta(&sm.a_ready[0], 0);  // a_ready[j] sits 8*j bytes further on
-      half_addr = tc::map_to_cta(&sm.a_half, 0);
-    }
     auto publish = [&](int j) {
-      if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
-      else fence_proxy_async();
+      fence_proxy_async();
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) {
-        if (PAIR) tc::mbar_arrive_cluster(ready_addr0 + 8u * (uint32_t)j);
-        else mbar_arrive(&sm.a_ready[j]);
-      }
+      if (lane == 0) mbar_arrive(&sm.a_ready[j]);
     };
-
     auto publish_half = [&]() {
-      if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
-      else fence_proxy_async();
+      fence_proxy_async();
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) {
-        if (PAIR) tc::mbar_arrive_cluster(half_addr);
-        else mbar_arrive(&sm.a_half);
-      }
+      if (lane == 0) mbar_arrive(&sm.a_half);
     };
     // first channel of this warp's g8-th group of 8 inside a 64-channel block
     auto col_of = [&](int g8) -> int { return (EPI & 2) ? g8 * 32 + hw * 8 : hw * 16 + g8 * 8; };
@@ -856,22 +864,27 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   if (const char* tp = getenv("E3DGE_RENDER_TRACE_PTR"))  // measurement aid, see RenderArgs::trace
     a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
   const int cl = render_cluster_size();
-  if (a.stash) return mode == 0 ? launch_tc_variant<0, 1, true>(a, stream) : launch_tc_variant<1, 1, true>(a, stream);
   static int epi = -1;
   if (epi < 0) {
-    const char* e = getenv("E3DGE_RENDER_EPI");  // measurement aid: epilogue code variant
+    // epilogue / MMA-issue variant (template parameter EPI): 3 = default, 7 = CTA pairs, 0 = the scalar
+    // epilogue the what-if flags and the multicast weight-stream clusters (E3DGE_RENDER_CLUSTER) apply to
+    const char* e = getenv("E3DGE_RENDER_EPI");
     epi = e ? atoi(e) : 3;
+    if (epi != 0 && epi != 7) epi = 3;
   }
-  if (mode == 0 && cl == 1 && !a.stash && epi == 1) return launch_tc_variant<0, 1, false, 1>(a, stream);
-  if (mode == 0 && cl == 1 && !a.stash && epi == 3) return launch_tc_variant<0, 1, false, 3>(a, stream);
-  if (mode == 0 && !a.stash && epi == 7) return launch_tc_variant<0, 2, false, 7>(a, stream);
+  // every variant computes each value with the same operations, but the sdf / rgb head sums follow the
+  // thread-to-column mapping: the training forward (stash) uses the mapping of the inference forward
+  if (a.stash) {
+    if (epi == 0) return mode == 0 ? launch_tc_variant<0, 1, true, 0>(a, stream) : launch_tc_variant<1, 1, true, 0>(a, stream);
+    return mode == 0 ? launch_tc_variant<0, 1, true, 3>(a, stream) : launch_tc_variant<1, 1, true, 3>(a, stream);
+  }
+  if (epi == 7) return mode == 0 ? launch_tc_variant<0, 2, false, 7>(a, stream) : launch_tc_variant<1, 2, false, 7>(a, stream);
+  if (epi == 3) return mode == 0 ? launch_tc_variant<0, 1, false, 3>(a, stream) : launch_tc_variant<1, 1, false, 3>(a, stream);
   if (mode == 0) {
     if (cl == 4) return launch_tc_variant<0, 4>(a, stream);
     if (cl == 2) return launch_tc_variant<0, 2>(a, stream);
     return launch_tc_variant<0, 1>(a, stream);
   }
-  if (cl == 4) return launch_tc_variant<1, 4>(a, stream);
-  if (cl == 2) return launch_tc_variant<1, 2>(a, stream);
   return launch_tc_variant<1, 1>(a, stream);
 }
 

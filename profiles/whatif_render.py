@@ -6,6 +6,7 @@
     whatever the ring holds and never wait for a tile) — numerically WRONG results.
 Run under gpurun:  for c in 1 2 4; do E3DGE_RENDER_CLUSTER=$c python profiles/whatif_render.py; done"""
 import os, sys, statistics
+os.environ.setdefault("E3DGE_RENDER_EPI", "0")  # the debug flags exist in the scalar-epilogue variant only
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "cvpr23-e3dge_b200"), os.path.join(ROOT, "tests")]
 import torch
