@@ -387,21 +387,28 @@ __global__ void __launch_bounds__(256) upconv_blur_act_kernel(const __grid_const
       const int pr = (r & 1) ^ 1;            // rows alternate odd, even, odd, ...
       const int i = y + ((r + 1) >> 1) - 1;  // y-1, y, y, y+1, y+1, y+2, y+2
       if (i < 0 || i >= a.H + (pr ? 0 : 1)) continue;
+      // the row's seven vectors are requested together (predicated, no branches between the loads): the
+      // kernel is bound by the number of loads in flight, not by bytes
+      float4 tv[7];
 #pragma unroll
       for (int c = 0; c < 7; ++c) {
         const int pc = (c & 1) ^ 1;
         const int j = x + ((c + 1) >> 1) - 1;
-        if (j < 0 || j >= a.W + (pc ? 0 : 1)) continue;
-        const float4 tv = *reinterpret_cast<const float4*>(
-            a.t + ((size_t)(pr * 2 + pc) * Mp + ((size_t)b * Hp + i) * Wp + j) * a.cout + o);
+        const bool ok = j >= 0 && j < a.W + (pc ? 0 : 1);
+        const float4* src = reinterpret_cast<const float4*>(
+            a.t + ((size_t)(pr * 2 + pc) * Mp + ((size_t)b * Hp + i) * Wp + (ok ? j : 0)) * a.cout + o);
+        tv[c] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
 #pragma unroll
         for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 4; ++kx) {
             const float k = blur_w(r, ky) * blur_w(c, kx);
             if (k != 0.f) {
-              acc[ky][kx].x = fmaf(k, tv.x, acc[ky][kx].x), acc[ky][kx].y = fmaf(k, tv.y, acc[ky][kx].y);
-              acc[ky][kx].z = fmaf(k, tv.z, acc[ky][kx].z), acc[ky][kx].w = fmaf(k, tv.w, acc[ky][kx].w);
+              acc[ky][kx].x = fmaf(k, tv[c].x, acc[ky][kx].x), acc[ky][kx].y = fmaf(k, tv[c].y, acc[ky][kx].y);
+              acc[ky][kx].z = fmaf(k, tv[c].z, acc[ky][kx].z), acc[ky][kx].w = fmaf(k, tv[c].w, acc[ky][kx].w);
             }
           }
       }

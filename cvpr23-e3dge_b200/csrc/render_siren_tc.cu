@@ -273,11 +273,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         for (int l = 0; l < gemm_layers; ++l) {
           if (EPI & 2) {
             mbar_wait(&sm.a_half, pa);
-            tc::mbar_arrive_cluster(half0);
+            tc::mbar_arrive_cluster_relaxed(half0);
           }
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&sm.a_ready[kb], pa);
-            tc::mbar_arrive_cluster(ready0 + 8u * (uint32_t)kb);
+            tc::mbar_arrive_cluster_relaxed(ready0 + 8u * (uint32_t)kb);
           }
           pa ^= 1;
         }
@@ -295,10 +295,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256;
           for (int kb = 0; kb < 4; ++kb) {
             // k-block kb of this layer's A operand is published
-            if (PAIR) {
-              if ((EPI & 2) && kb == 0) tc::mbar_wait_cluster(&sm.a_half, pa);
-              else tc::mbar_wait_cluster(&sm.a_ready[kb], pa);
-            } else if ((EPI & 2) && kb == 0) {
+            if ((EPI & 2) && kb == 0) {
               mbar_wait(&sm.a_half, pa);
             } else {
               mbar_wait(&sm.a_ready[kb], pa);
@@ -322,8 +319,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 if ((EPI & 2) && kb == 0 && pr == 0 && ks == 2) {  // second half of block 0
-                  if (PAIR) tc::mbar_wait_cluster(&sm.a_ready[0], pa);
-                  else mbar_wait(&sm.a_ready[0], pa);
+                  mbar_wait(&sm.a_ready[0], pa);
                   tc::fence_after_thread_sync();
                 }
                 const uint64_t bk = tc::advance_desc_k(dB, ks);

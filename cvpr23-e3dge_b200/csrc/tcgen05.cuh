@@ -81,6 +81,13 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The release form above costs ~1.5k cycles (a cluster-scope fence).  The forwarder thread of the paired
+// render kernel has nothing of its own to publish: the data are shared-memory stores of OTHER threads
+// that already performed (proxy fence + CTA-scope release-arrive, acquired by this thread) and are read by
+// the tensor core of the SM that holds them.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
