@@ -64,6 +64,7 @@ struct SmemTC {
   uint64_t full[TC_RING], empty[TC_RING];
   uint64_t a_ready[4], d_ready;
   uint64_t a_half;  // EPI bit 1: channels [0,32) of block 0 are published (the next layer's first MMAs start)
+  uint64_t a_tail;  // pairs: channels [192,224) of block 3 are published (half of the last k-block's MMAs start)
   uint32_t tmem_slot;
 };
 static_assert(sizeof(SmemTC) + 1024 <= 227 * 1024, "shared memory budget");
@@ -190,13 +191,13 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], PAIR ? 1 : CL);
     }
-#pragma unroll
-    // pairs: the leader's barriers also take one arrival per phase from the peer CTA's forwarder thread
-    const uint32_t n_arrive = TC_COMPUTE_WARPS + ((PAIR && leader) ? 1 : 0);
+    // pairs: the epilogue warps of BOTH CTAs arrive on the leader's barriers
+    const uint32_t n_arrive = (PAIR ? 2 : 1) * TC_COMPUTE_WARPS;
 #pragma unroll
     for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], n_arrive);
     mbar_init(&sm.d_ready, 1);
     mbar_init(&sm.a_half, n_arrive);
+    mbar_init(&sm.a_tail, n_arrive);
     fence_mbar_init();
   }
   for (int i = tid; i < SW; i += TC_NTHREADS) sm.wsig[i] = a.packed[OFF_WSIG + i];
@@ -263,28 +264,71 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (PAIR && !leader && lane == 0) {
-      // ===== peer CTA: forward "this CTA's epilogue warps have published" to the leader's barriers =====
-      // (the epilogue warps arrive locally — a remote release-arrive from each of them costs ~1k cycles
-      // on their critical path; here one otherwise idle thread pays it)
-      const uint32_t ready0 = tc::map_to_cta(&sm.a_ready[0], 0), half0 = tc::map_to_cta(&sm.a_half, 0);
-      uint32_t pa = 0;
+    if (PAIR && leader && lane == 0) {
+      // ===== CTA pair: one tcgen05.mma cta_group::2 stream over both CTAs' tiles (M = 256) =====
+      // A k-block's 12 MMAs use two ring stages (W_hi block, W_lo block).  Blocks 0 and 3 arrive in two
+      // halves (a_half / a_tail, then a_ready): the k-steps of the first half are issued for both weight
+      // blocks before the second half is waited for, so the head of a layer starts, and the tail after the
+      // epilogue's last publish shrinks, by half a block.
+      const uint32_t idesc = tc::make_idesc_bf16_f32(256, 256);
+      const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
+      uint32_t stage = 0, phase = 0, pa = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
+        const bool tr = a.trace && blockIdx.x == 0 && t == 1;
         for (int l = 0; l < gemm_layers; ++l) {
-          if (EPI & 2) {
-            mbar_wait(&sm.a_half, pa);
-            tc::mbar_arrive_cluster_relaxed(half0);
-          }
+          const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256;
           for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&sm.a_ready[kb], pa);
-            tc::mbar_arrive_cluster_relaxed(ready0 + 8u * (uint32_t)kb);
+            const bool split = kb == 0 || kb == 3;
+            mbar_wait(kb == 0 ? &sm.a_half : (kb == 3 ? &sm.a_tail : &sm.a_ready[kb]), pa);
+            if (tr) a.trace[128 + l * 8 + kb] = clock64();
+            tc::fence_after_thread_sync();
+            const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
+            const uint64_t dAl = tc::make_smem_desc_sw128(a_lo0 + kb * A_KBLOCK_BYTES);
+            const uint64_t dB0 = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
+            const uint64_t dB1 = tc::make_smem_desc_sw128(smem_u32(sm.ring + (stage + 1) * TC_TILE_BYTES));
+            auto hi_block = [&](int ks) {  // h_hi * W_hi + h_lo * W_hi
+              const uint64_t bk = tc::advance_desc_k(dB0, ks);
+              tc::mma_bf16_ss_pair(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
+              tc::mma_bf16_ss_pair(dcol, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+            };
+            auto lo_block = [&](int ks) {  // h_hi * W_lo
+              tc::mma_bf16_ss_pair(dcol, tc::advance_desc_k(dAh, ks), tc::advance_desc_k(dB1, ks), idesc, true);
+            };
+            mbar_wait(&sm.full[stage], phase);
+            tc::fence_after_thread_sync();
+            if (split) {
+              hi_block(0), hi_block(1);
+              mbar_wait(&sm.full[stage + 1], phase);
+              tc::fence_after_thread_sync();
+              lo_block(0), lo_block(1);
+              mbar_wait(&sm.a_ready[kb], pa);  // second half of the block
+              tc::fence_after_thread_sync();
+              hi_block(2), hi_block(3);
+              tc::mma_commit_pair(&sm.empty[stage], 3);
+              lo_block(2), lo_block(3);
+              tc::mma_commit_pair(&sm.empty[stage + 1], 3);
+            } else {
+              hi_block(0), hi_block(1), hi_block(2), hi_block(3);
+              tc::mma_commit_pair(&sm.empty[stage], 3);
+              mbar_wait(&sm.full[stage + 1], phase);
+              tc::fence_after_thread_sync();
+              lo_block(0), lo_block(1), lo_block(2), lo_block(3);
+              tc::mma_commit_pair(&sm.empty[stage + 1], 3);
+            }
+            if (tr) a.trace[256 + l * 16 + kb * 4 + 3] = clock64();
+            stage += 2;
+            if (stage == TC_RING) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
           pa ^= 1;
+          tc::mma_commit_pair(&sm.d_ready, 3);
         }
       }
     }
-    if (lane == 0 && leader) {
-      const uint32_t idesc = tc::make_idesc_bf16_f32(PAIR ? 256 : 128, 256);
+    if (!PAIR && lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16_f32(128, 256);
       const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
       const bool skip_lo = (a.p.flags & DBG_SKIP_LO_MMA) != 0;
       const bool no_w = (a.p.flags & DBG_NO_WSTREAM) != 0;
@@ -312,7 +356,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             for (int pr = 0; pr < 2; ++pr) {  // pr 0: W_hi block, pr 1: W_lo block
               if (!no_w) {
                 mbar_wait(&sm.full[stage], phase);
-                if (!PAIR) mbar_wait(&sm.full[stage + 1], phase);
+                mbar_wait(&sm.full[stage + 1], phase);
               }
               tc::fence_after_thread_sync();
               const uint64_t dB = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * TC_TILE_BYTES));
@@ -323,25 +367,13 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
                   tc::fence_after_thread_sync();
                 }
                 const uint64_t bk = tc::advance_desc_k(dB, ks);
-                auto mma = [&](uint64_t da, bool accum) {
-                  if (PAIR) tc::mma_bf16_ss_pair(dcol, da, bk, idesc, accum);
-                  else tc::mma_bf16_ss(dcol, da, bk, idesc, accum);
-                };
+                auto mma = [&](uint64_t da, bool accum) { tc::mma_bf16_ss(dcol, da, bk, idesc, accum); };
                 if (pr == 0) {
                   mma(tc::advance_desc_k(dAh, ks), (kb | ks) != 0);
                   if (!skip_lo) mma(tc::advance_desc_k(dAl, ks), true);
                 } else if (!skip_lo) {
                   mma(tc::advance_desc_k(dAh, ks), true);
                 }
-              }
-              if (PAIR) {
-                if (!no_w) tc::mma_commit_pair(&sm.empty[stage], 3);
-                if (tr) a.trace[256 + l * 16 + kb * 4 + pr * 2 + 1] = clock64();
-                if (++stage == TC_RING) {
-                  stage = 0;
-                  phase ^= 1;
-                }
-                continue;
               }
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -358,8 +390,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             }
           }
           pa ^= 1;  // each a_ready[kb] completes exactly once per layer
-          if (PAIR) tc::mma_commit_pair(&sm.d_ready, 3);
-          else tc::mma_commit(&sm.d_ready);
+          tc::mma_commit(&sm.d_ready);
         }
       }
     }
@@ -379,17 +410,28 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     const bool no_sin = (P.flags & DBG_NO_SIN) != 0;
 
     // publish k-block j of the next A operand: generic-proxy stores -> async proxy (UMMA)
-    auto publish = [&](int j) {
+    // Pairs: every arrival goes to the LEADER's barrier.  The peer's warps arrive remotely with a relaxed
+    // arrive: the release form is a cluster-scope fence (~1.5k cycles on the critical path, measured), and
+    // there is nothing left to order — the proxy fence has completed this warp's shared-memory stores, and
+    // they are read by the tensor core of the SM that holds them.
+    const bool remote = PAIR && !leader;
+    const uint32_t ready0 = remote ? tc::map_to_cta(&sm.a_ready[0], 0) : 0;  // a_ready[j] is 8*j bytes on
+    const uint32_t half_addr = remote ? tc::map_to_cta(&sm.a_half, 0) : 0;
+    const uint32_t tail_addr = remote ? tc::map_to_cta(&sm.a_tail, 0) : 0;
+    auto publish_on = [&](uint64_t* bar, uint32_t remote_addr) {
       fence_proxy_async();
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.a_ready[j]);
+      if (lane == 0) {
+        if (remote) tc::mbar_arrive_cluster_relaxed(remote_addr);
+        else mbar_arrive(bar);
+      }
     };
-    auto publish_half = [&]() {
-      fence_proxy_async();
-      tc::fence_before_thread_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.a_half);
+    auto publish = [&](int j) { publish_on(&sm.a_ready[j], ready0 + 8u * (uint32_t)j); };
+    // first 8 channels of block j are stored: the half-block barriers of blocks 0 (and, in pairs, 3)
+    auto publish_first_half = [&](int j) {
+      if ((EPI & 2) && j == 0) publish_on(&sm.a_half, half_addr);
+      if (PAIR && j == 3) publish_on(&sm.a_tail, tail_addr);
     };
     // first channel of this warp's g8-th group of 8 inside a 64-channel block
     auto col_of = [&](int g8) -> int { return (EPI & 2) ? g8 * 32 + hw * 8 : hw * 16 + g8 * 8; };
@@ -522,7 +564,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           }
           store_a8(sm, m, n0, v);
           if (taps) store_tap(0, n0, v);
-          if ((EPI & 2) && j == 0 && g8 == 0) publish_half();
+          if (g8 == 0) publish_first_half(j);
         }
         publish(j);
         if (tr) a.trace[1 + j] = clock64();
@@ -607,7 +649,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             }
             if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
             if (feed) store_a8_v<EPI>(sm, m, n0, v);
-            if ((EPI & 2) && feed && j == 0 && g8 == 0) publish_half();
+            if (feed && g8 == 0) publish_first_half(j);
             if (tr && l == 3) a.trace[384 + j * 8 + 2 + g8 * 2] = clock64();
           }
           if (feed) publish(j);
