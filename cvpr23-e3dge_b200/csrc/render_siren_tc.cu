@@ -239,9 +239,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               phase ^= 1;
             }
           }
-          continue;
         }
-        for (int c = 0; c < per_tile; ++c) {
+        for (int c = 0; c < (PAIR ? 0 : per_tile); ++c) {
           mbar_wait(&sm.empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&sm.full[stage], TC_TILE_BYTES);
           if (CL == 1 && use_wmap) {
@@ -405,6 +404,9 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     const int S = (MODE == 0) ? P.n_samples : 1;
     const int HW = (MODE == 0) ? P.height * P.width : a.n_points;
     const float* pk = a.packed;
+    float* w0s = &sm.rgb_part[0][0][0];   // [3][256] layer-0 weights (start of a tile)
+    float* wvs = &sm.film[0][0][0];       // [6][256] W_dir rows, W_rgb rows (end of a tile, FiLM rows 0..2)
+    static_assert(sizeof(sm.rgb_part) >= 3 * SW * sizeof(float) && 3 * 2 * SW == 6 * SW, "aliases");
     uint32_t pd = 0;
     int cur_b = -1;
     const bool no_sin = (P.flags & DBG_NO_SIN) != 0;
@@ -449,13 +451,17 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       const bool valid = m < n_valid;
       const int r = valid ? m / S : 0, s = valid ? m - r * S : 0;
 
-      if (b != cur_b) {  // FiLM table of this image -> shared memory (rows gamma, beta')
+      {  // FiLM table of this image -> shared memory (rows gamma, beta'); the previous tile's view-layer
+         // epilogue parked W_dir / W_rgb in the rows of layers 0..2, so those come back every tile
         const float* f = a.in.film + (size_t)b * 9 * FILM_ROWS * SW;
-        for (int i = ct; i < 9 * 2 * SW; i += TC_COMPUTE) {
+        const int n_layers = (b != cur_b) ? 9 : (a.with_view ? 3 : 0);
+        for (int i = ct; i < n_layers * 2 * SW; i += TC_COMPUTE) {
           const int l = i / (2 * SW), row = (i / SW) & 1, n = i % SW;
           sm.film[l][row][n] = f[(l * FILM_ROWS + (row ? 2 : 0)) * SW + n];
         }
         cur_b = b;
+        // layer-0 weights [3][256] live in the rgb_part array, which is only used at the end of a tile
+        for (int i = ct; i < 3 * SW; i += TC_COMPUTE) w0s[i] = __ldg(pk + OFF_W0N + i);
       }
 
       // ---- per-row geometry, recomputed by both column halves ----
@@ -550,9 +556,9 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
           for (int i4 = 0; i4 < 2; ++i4) {
             const int n = n0 + i4 * 4;
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + n));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + SW + n));
-            const float4 w2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_W0N + 2 * SW + n));
+            const float4 w0 = *reinterpret_cast<const float4*>(w0s + n);
+            const float4 w1 = *reinterpret_cast<const float4*>(w0s + SW + n);
+            const float4 w2 = *reinterpret_cast<const float4*>(w0s + 2 * SW + n);
             const float a4[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
                                  fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
 #pragma unroll
@@ -660,6 +666,13 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       }
       sm.sdf_part[hw][m] = sdf_acc;
       compute_sync();
+      if (a.with_view) {  // every warp is past layer 7: FiLM rows 0..2 are free until the next tile
+        for (int i = ct; i < 3 * SW; i += TC_COMPUTE) {
+          wvs[i] = __ldg(pk + OFF_WVDN + i);
+          wvs[3 * SW + i] = __ldg(pk + OFF_WRGB + i);
+        }
+        if (MODE != 0) compute_sync();  // (MODE 0 has the barriers of the alpha / scan steps in between)
+      }
 
       // ---- sdf -> sigma -> alpha -> transmittance scan (overlaps the view-layer MMAs) ----
       if (MODE == 0) {
@@ -737,12 +750,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const int n = nb + j4 * 4;
-            const float4 d0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + n));
-            const float4 d1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + SW + n));
-            const float4 d2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WVDN + 2 * SW + n));
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + n));
-            const float4 r1 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + SW + n));
-            const float4 r2 = __ldg(reinterpret_cast<const float4*>(pk + OFF_WRGB + 2 * SW + n));
+            const float4 d0 = *reinterpret_cast<const float4*>(wvs + n);
+            const float4 d1 = *reinterpret_cast<const float4*>(wvs + SW + n);
+            const float4 d2 = *reinterpret_cast<const float4*>(wvs + 2 * SW + n);
+            const float4 r0 = *reinterpret_cast<const float4*>(wvs + 3 * SW + n);
+            const float4 r1 = *reinterpret_cast<const float4*>(wvs + 4 * SW + n);
+            const float4 r2 = *reinterpret_cast<const float4*>(wvs + 5 * SW + n);
             const float e0[4] = {d0.x, d0.y, d0.z, d0.w}, e1[4] = {d1.x, d1.y, d1.z, d1.w},
                         e2[4] = {d2.x, d2.y, d2.z, d2.w};
             const float q0[4] = {r0.x, r0.y, r0.z, r0.w}, q1[4] = {r1.x, r1.y, r1.z, r1.w},
@@ -804,15 +817,20 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             }
             a.out.thumb_rgb[((size_t)b * 3 + c) * HW + unit0 + rr] = -1.f + 2.f * accum;
           }
-          if (a.out.features && ct < SW) {
-            const int n = ct;  // one output channel per thread (first 256 compute threads)
+          if (a.out.features) {
+            const int n = ct & (SW - 1);  // one output channel per thread pair: even / odd rays
             const float* row = fbuf + n * TCM;
             const int sw = n & 31;
             float* o = a.out.features + ((size_t)b * SW + n) * HW + unit0;
-            for (int rr = 0; rr < n_units; ++rr) {
-              float accum = 0.f;
-              for (int si = 0; si < S; ++si) accum += row[(rr * S + si) ^ sw];
-              o[rr] = accum;
+            for (int rr = ct >> 8; rr < n_units; rr += 2) {
+              float acc0 = 0.f, acc1 = 0.f;  // two chains: the shared-memory latency overlaps
+              int si = 0;
+              for (; si + 1 < S; si += 2) {
+                acc0 += row[(rr * S + si) ^ sw];
+                acc1 += row[(rr * S + si + 1) ^ sw];
+              }
+              if (si < S) acc0 += row[(rr * S + si) ^ sw];
+              o[rr] = acc0 + acc1;
             }
           }
         } else if (a.p_rgb && hw == 0 && valid) {
@@ -904,17 +922,20 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   const int cl = render_cluster_size();
   static int epi = -1;
   if (epi < 0) {
-    // epilogue / MMA-issue variant (template parameter EPI): 3 = default, 7 = CTA pairs, 0 = the scalar
-    // epilogue the what-if flags and the multicast weight-stream clusters (E3DGE_RENDER_CLUSTER) apply to
+    // epilogue / MMA-issue variant (template parameter EPI): 7 = CTA pairs (default), 3 = one CTA per
+    // MMA stream, 0 = the scalar epilogue the what-if flags and the multicast weight-stream clusters
+    // (E3DGE_RENDER_CLUSTER) apply to
     const char* e = getenv("E3DGE_RENDER_EPI");
-    epi = e ? atoi(e) : 3;
-    if (epi != 0 && epi != 7) epi = 3;
+    epi = e ? atoi(e) : 7;
+    if (epi != 0 && epi != 3) epi = 7;
   }
-  // every variant computes each value with the same operations, but the sdf / rgb head sums follow the
-  // thread-to-column mapping: the training forward (stash) uses the mapping of the inference forward
+  // every variant computes each value with the same operations, but the order of the accumulations (MMA
+  // issue order, head sums per thread-to-column mapping) differs: the training forward (stash) is the
+  // same variant as the inference forward, so that the two agree bit for bit
   if (a.stash) {
     if (epi == 0) return mode == 0 ? launch_tc_variant<0, 1, true, 0>(a, stream) : launch_tc_variant<1, 1, true, 0>(a, stream);
-    return mode == 0 ? launch_tc_variant<0, 1, true, 3>(a, stream) : launch_tc_variant<1, 1, true, 3>(a, stream);
+    if (epi == 3) return mode == 0 ? launch_tc_variant<0, 1, true, 3>(a, stream) : launch_tc_variant<1, 1, true, 3>(a, stream);
+    return mode == 0 ? launch_tc_variant<0, 2, true, 7>(a, stream) : launch_tc_variant<1, 2, true, 7>(a, stream);
   }
   if (epi == 7) return mode == 0 ? launch_tc_variant<0, 2, false, 7>(a, stream) : launch_tc_variant<1, 2, false, 7>(a, stream);
   if (epi == 3) return mode == 0 ? launch_tc_variant<0, 1, false, 3>(a, stream) : launch_tc_variant<1, 1, false, 3>(a, stream);
