@@ -269,7 +269,7 @@ def kernel_roofline(G, inp, dev, flush, args):
             traffic = json.load(fh).get("dram_bytes_per_launch")
     tf32_equiv = RENDER_FLOP_PER_IMAGE * BATCH / (ms_fp32 / 1e3) / 1e12
     return {"roofline": {
-        "kernel": "siren_render_tc_kernel<0>", "bound": "tensor", "achieved": tflops,
+        "kernel": "siren_render_tc_kernel<0, 2, false, 7> (CTA pairs, tcgen05 cta_group::2)", "bound": "tensor", "achieved": tflops,
         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_tflops"],
         "traffic": traffic, "peak_source": how + " (cuBLAS bf16 burst)", "kernel_ms": ms,
         "executed_tflops": executed,
