@@ -559,16 +559,33 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             const float4 w0 = *reinterpret_cast<const float4*>(w0s + n);
             const float4 w1 = *reinterpret_cast<const float4*>(w0s + SW + n);
             const float4 w2 = *reinterpret_cast<const float4*>(w0s + 2 * SW + n);
+            if (EPI & 1) {
+              const float4 g4 = *reinterpret_cast<const float4*>(&sm.film[0][0][n]);
+              const float4 b4 = *reinterpret_cast<const float4*>(&sm.film[0][1][n]);
+              const f32x2 X0 = pk2(x0, x0), X1 = pk2(x1, x1), X2 = pk2(x2, x2), Z = pk2(0.f, 0.f);
+              const f32x2 pa = fma2(pk2(w2.x, w2.y), X2, fma2(pk2(w1.x, w1.y), X1, fma2(pk2(w0.x, w0.y), X0, Z)));
+              const f32x2 pb = fma2(pk2(w2.z, w2.w), X2, fma2(pk2(w1.z, w1.w), X1, fma2(pk2(w0.z, w0.w), X0, Z)));
+              f32x2 a0, a1;
+              film_sin2(pa, pk2(g4.x, g4.y), pk2(b4.x, b4.y), v[i4 * 4], v[i4 * 4 + 1], a0);
+              film_sin2(pb, pk2(g4.z, g4.w), pk2(b4.z, b4.w), v[i4 * 4 + 2], v[i4 * 4 + 3], a1);
+              if (STASH && stash) {
+                float t0, t1, t2, t3;
+                unpk2(a0, t0, t1);
+                unpk2(a1, t2, t3);
+                float* sp = stash + (size_t)n * TCM;
+                sp[0] = t0, sp[TCM] = t1, sp[2 * TCM] = t2, sp[3 * TCM] = t3;
+              }
+            }
             const float a4[4] = {fmaf(w2.x, x2, fmaf(w1.x, x1, w0.x * x0)), fmaf(w2.y, x2, fmaf(w1.y, x1, w0.y * x0)),
                                  fmaf(w2.z, x2, fmaf(w1.z, x1, w0.z * x0)), fmaf(w2.w, x2, fmaf(w1.w, x1, w0.w * x0))};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < ((EPI & 1) ? 0 : 4); ++i) {
               const float arg = fmaf(sm.film[0][0][n + i], a4[i], sm.film[0][1][n + i]);
               if (STASH && stash) stash[(size_t)(n + i) * TCM] = arg;
               v[i4 * 4 + i] = sin_mufu_reduced(arg);
             }
           }
-          store_a8(sm, m, n0, v);
+          store_a8_v<EPI>(sm, m, n0, v);
           if (taps) store_tap(0, n0, v);
           if (g8 == 0) publish_first_half(j);
         }
@@ -593,70 +610,93 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           la = a.in.local_alpha + (samp0 + m) * SW;
           lb = a.in.local_beta + (samp0 + m) * SW;
         }
+        // one group = 8 channels of this thread's row: FiLM + sin (pre-activations acc8), heads, taps,
+        // hi/lo split and store into the next A operand, first-half publish
+        auto finish_group = [&](int j, int g8, int n0, float* v) {
+          if (tr && l == 3) a.trace[384 + j * 8 + 1 + g8 * 2] = clock64();
+          if (last) {
+            // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sdf_acc = fmaf(sm.wsig[n0 + i], v[i], sdf_acc);
+            if (la) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + i], 1.f), v[i]), lb[n0 + i]);
+            }
+          }
+          if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
+          if (feed) store_a8_v<EPI>(sm, m, n0, v);
+          if (feed && g8 == 0) publish_first_half(j);
+          if (tr && l == 3) a.trace[384 + j * 8 + 2 + g8 * 2] = clock64();
+        };
+        auto packed_group = [&](int j, int g8, const uint32_t* r8, const float4* g2, const float4* b2) {
+          const int n0 = j * 64 + col_of(g8);
+          float v[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 g4 = g2[h], b4 = b2[h];
+            f32x2 a0, a1;
+            film_sin2(pk2u(r8[h * 4], r8[h * 4 + 1]), pk2(g4.x, g4.y), pk2(b4.x, b4.y), v[h * 4], v[h * 4 + 1], a0);
+            film_sin2(pk2u(r8[h * 4 + 2], r8[h * 4 + 3]), pk2(g4.z, g4.w), pk2(b4.z, b4.w), v[h * 4 + 2],
+                      v[h * 4 + 3], a1);
+            if (STASH && stash) {
+              float t0, t1, t2, t3;
+              unpk2(a0, t0, t1);
+              unpk2(a1, t2, t3);
+              float* sp = stash + (size_t)(l * SW + n0 + h * 4) * TCM;
+              sp[0] = t0, sp[TCM] = t1, sp[2 * TCM] = t2, sp[3 * TCM] = t3;
+            }
+          }
+          finish_group(j, g8, n0, v);
+        };
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-          float acc[16];
-          float4 fg[4], fb[4];
           if (EPI & 1) {
             uint32_t accr[16];
-            if (EPI & 2) tc::tmem_ld_2x32x8_issue(dsrc0 + j * 64 + hw * 8, accr);
-            else tc::tmem_ld_32x16_issue(dsrc + j * 64, accr);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            float4 fg[4], fb[4];
+            auto film_rows = [&](int i) {
               const int n = j * 64 + col_of(i >> 1) + (i & 1) * 4;
               fg[i] = *reinterpret_cast<const float4*>(&sm.film[l][0][n]);
               fb[i] = *reinterpret_cast<const float4*>(&sm.film[l][1][n]);
-            }
-            tc::tmem_ld_wait16(accr);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(accr[i]);
-          } else {
-            tc::tmem_ld_32x16(dsrc + j * 64, acc);
-          }
-          if (tr && l == 3) a.trace[384 + j * 8] = clock64();
-#pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            const int n0 = j * 64 + col_of(g8);
-            float v[8];
-            if (EPI & 1) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float4 g4 = fg[g8 * 2 + h], b4 = fb[g8 * 2 + h];
-                const int c = g8 * 8 + h * 4;
-                f32x2 a0, a1;
-                film_sin2(pk2(acc[c], acc[c + 1]), pk2(g4.x, g4.y), pk2(b4.x, b4.y), v[h * 4], v[h * 4 + 1], a0);
-                film_sin2(pk2(acc[c + 2], acc[c + 3]), pk2(g4.z, g4.w), pk2(b4.z, b4.w), v[h * 4 + 2], v[h * 4 + 3], a1);
-                if (STASH && stash) {
-                  float t0, t1, t2, t3;
-                  unpk2(a0, t0, t1);
-                  unpk2(a1, t2, t3);
-                  float* sp = stash + (size_t)(l * SW + n0 + h * 4) * TCM;
-                  sp[0] = t0, sp[TCM] = t1, sp[2 * TCM] = t2, sp[3 * TCM] = t3;
-                }
-              }
+            };
+            if (EPI & 2) {
+              // TMEM reads run at ~64 B/clk per SM: sixteen warps asking for 16 columns each wait ~500
+              // cycles.  The 8 columns of the first half-block are requested alone, the other 8 land under
+              // their processing.
+              tc::tmem_ld_32x8_issue(dsrc0 + j * 64 + hw * 8, accr);
+              film_rows(0), film_rows(1);
+              tc::tmem_ld_wait8(accr);
+              tc::tmem_ld_32x8_issue(dsrc0 + j * 64 + 32 + hw * 8, accr + 8);
+              film_rows(2), film_rows(3);
+              if (tr && l == 3) a.trace[384 + j * 8] = clock64();
+              packed_group(j, 0, accr, fg, fb);
+              tc::tmem_ld_wait8(accr + 8);
+              packed_group(j, 1, accr + 8, fg + 2, fb + 2);
             } else {
+              tc::tmem_ld_32x16_issue(dsrc + j * 64, accr);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) film_rows(i);
+              tc::tmem_ld_wait16(accr);
+              if (tr && l == 3) a.trace[384 + j * 8] = clock64();
+              packed_group(j, 0, accr, fg, fb);
+              packed_group(j, 1, accr + 8, fg + 2, fb + 2);
+            }
+          } else {
+            float acc[16];
+            tc::tmem_ld_32x16(dsrc + j * 64, acc);
+            if (tr && l == 3) a.trace[384 + j * 8] = clock64();
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              const int n0 = j * 64 + col_of(g8);
+              float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float arg = fmaf(sm.film[l][0][n0 + i], acc[g8 * 8 + i], sm.film[l][1][n0 + i]);
                 if (STASH && stash) stash[(size_t)(l * SW + n0 + i) * TCM] = arg;
                 v[i] = no_sin ? arg * 1e-3f : sin_mufu_reduced(arg);
               }
+              finish_group(j, g8, n0, v);
             }
-            if (tr && l == 3) a.trace[384 + j * 8 + 1 + g8 * 2] = clock64();
-            if (last) {
-              // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) sdf_acc = fmaf(sm.wsig[n0 + i], v[i], sdf_acc);
-              if (la) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  v[i] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + i], 1.f), v[i]), lb[n0 + i]);
-              }
-            }
-            if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
-            if (feed) store_a8_v<EPI>(sm, m, n0, v);
-            if (feed && g8 == 0) publish_first_half(j);
-            if (tr && l == 3) a.trace[384 + j * 8 + 2 + g8 * 2] = clock64();
           }
           if (feed) publish(j);
           if (tr && l == 3) a.trace[384 + j * 8 + 5] = clock64();
@@ -742,6 +782,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         const float wrow = (MODE == 0 && valid) ? sm.wgt[m] : 0.f;
         float* fbuf = reinterpret_cast<float*>(sm.a_hi);  // [256][128] fp32 over a_hi + a_lo
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        f32x2 C0 = pk2(0.f, 0.f), C1 = C0, C2 = C0;  // packed rgb-head sums (even, odd channels)
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           float acc[16];
@@ -760,8 +801,36 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
                         e2[4] = {d2.x, d2.y, d2.z, d2.w};
             const float q0[4] = {r0.x, r0.y, r0.z, r0.w}, q1[4] = {r1.x, r1.y, r1.z, r1.w},
                         q2[4] = {r2.x, r2.y, r2.z, r2.w};
+            if (EPI & 1) {  // two channels per instruction
+              const float4 g4 = *reinterpret_cast<const float4*>(&sm.film[8][0][n]);
+              const float4 b4 = *reinterpret_cast<const float4*>(&sm.film[8][1][n]);
+              const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+              const f32x2 V0 = pk2(v0, v0), V1 = pk2(v1, v1), V2 = pk2(v2, v2);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+              for (int h = 0; h < 2; ++h) {
+                const int i = 2 * h;
+                f32x2 pre = pk2(acc[j4 * 4 + i], acc[j4 * 4 + i + 1]);
+                pre = fma2(pk2(e0[i], e0[i + 1]), V0, pre);
+                pre = fma2(pk2(e1[i], e1[i + 1]), V1, pre);
+                pre = fma2(pk2(e2[i], e2[i + 1]), V2, pre);
+                float f0, f1;
+                f32x2 arg8;
+                film_sin2(pre, pk2(gg[i], gg[i + 1]), pk2(bb[i], bb[i + 1]), f0, f1, arg8);
+                if (STASH && stash) {
+                  float t0, t1;
+                  unpk2(arg8, t0, t1);
+                  stash[(size_t)(8 * SW + n + i) * TCM] = t0;
+                  stash[(size_t)(8 * SW + n + i + 1) * TCM] = t1;
+                }
+                const f32x2 ff = pk2(f0, f1);
+                C0 = fma2(pk2(q0[i], q0[i + 1]), ff, C0);
+                C1 = fma2(pk2(q1[i], q1[i + 1]), ff, C1);
+                C2 = fma2(pk2(q2[i], q2[i + 1]), ff, C2);
+                acc[j4 * 4 + i] = f0, acc[j4 * 4 + i + 1] = f1;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < ((EPI & 1) ? 0 : 4); ++i) {
               float pre = acc[j4 * 4 + i];
               pre = fmaf(e0[i], v0, pre);
               pre = fmaf(e1[i], v1, pre);
@@ -791,6 +860,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               fbuf[n * TCM + (m ^ (n & 31))] = wrow * acc[i];
             }
           }
+        }
+        if (EPI & 1) {
+          float lo, hi;
+          unpk2(C0, lo, hi), c0 = lo + hi;
+          unpk2(C1, lo, hi), c1 = lo + hi;
+          unpk2(C2, lo, hi), c2 = lo + hi;
         }
         sm.rgb_part[hw][0][m] = c0;
         sm.rgb_part[hw][1][m] = c1;

@@ -216,6 +216,20 @@ __device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, uint32_t (&r
       : "r"(taddr)
       : "memory");
 }
+// split 32x8 load: `issue` starts it, `wait8` blocks until every outstanding tcgen05.ld of this thread
+// has landed and ties the 8 registers to that point
+__device__ __forceinline__ void tmem_ld_32x8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
 // two 32x8 loads, columns [c, c+8) and [c+32, c+40), into r[0..7] and r[8..15]
 __device__ __forceinline__ void tmem_ld_2x32x8_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
