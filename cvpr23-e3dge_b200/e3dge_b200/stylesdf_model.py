@@ -293,10 +293,14 @@ class ModulatedConv2d(nn.Module):
         self.backend = "auto"
         self._packed = _PackedConv()
         self._packed_bwd = _PackedConv()
+        self._prefetched = None  # ((latent ptr, batch), s, d) left by Decoder.prepare for the next call
 
     def styles(self, latent):
         """s [B,cin] and (if demodulating) d [B,cout] for latent [B,512] (may be a strided
         view latent[:, i] of [B,n_latent,512])."""
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None and pre[0] == (latent.data_ptr(), latent.shape[0]):
+            return pre[1], pre[2]
         lib = _lib.load()
         if latent.stride(-1) != 1 or latent.dtype != torch.float32 or not latent.is_cuda:
             latent = _lib.as_f32c(latent)
@@ -553,17 +557,54 @@ class Decoder(nn.Module):
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
         return latent, noise
 
+    def _layer_latents(self):
+        """(ModulatedConv2d, latent index) in execution order (stylesdf_model.py:764-795)."""
+        out = [(self.conv1.conv, 0), (self.to_rgb1.conv, 1)]
+        i = 1
+        for conv1, conv2, to_rgb in zip(self.convs[::2], self.convs[1::2], self.to_rgbs):
+            out += [(conv1.conv, i), (conv2.conv, i + 1), (to_rgb.conv, i + 2)]
+            i += 2
+        return out
+
+    def prepare(self, styles, batch, noise=None, inject_index=None, truncation=1, truncation_latent=None,
+                input_is_latent=False, randomize_noise=True):
+        """Everything of a pass that does not depend on the feature map: the latent (mapping network,
+        truncation, style mixing), every layer's modulation s / demodulation d, and the fresh noise maps —
+        about 25 tiny latency-bound launches.  G_pred_latents issues them on a side stream while the render
+        kernel runs; `forward(prepared=...)` consumes the result."""
+        assert isinstance(styles, list), "wrap latent code with list"
+        latent, noise = self.styles_and_noise_forward(styles, noise, inject_index, truncation,
+                                                      truncation_latent, input_is_latent, randomize_noise)
+        latent = _lib.as_f32c(latent)
+        keep = [latent]
+        for conv, idx in self._layer_latents():
+            lat = latent[:, idx]
+            conv._prefetched = None
+            s, d = conv.styles(lat)
+            conv._prefetched = ((lat.data_ptr(), lat.shape[0]), s, d)
+            keep += [s] if d is None else [s, d]
+        noise = list(noise)
+        for k in range(self.num_layers):
+            if noise[k] is None:  # fresh noise per call (stylesdf_model.py:461-462)
+                res = 2 ** ((k + 2 * self.log_in_size + 1) // 2)
+                noise[k] = torch.empty(batch, 1, res, res, device=latent.device).normal_()
+                keep.append(noise[k])
+        return latent, noise, keep
+
     def forward(self, features, styles, rgbd_in=None, transform=None, return_latents=False,
                 inject_index=None, truncation=1, truncation_latent=None, input_is_latent=False,
-                noise=None, randomize_noise=True, mesh_path=None, conditions=None):
+                noise=None, randomize_noise=True, mesh_path=None, conditions=None, prepared=None):
         """features [B,256,R,R] NCHW -> (image [B,3,size,size], latent|None)
         — stylesdf_model.py:742-797.  `conditions` is accepted and ignored exactly as in the
         reference (its HFGI hook is dead code)."""
         assert isinstance(styles, list), "wrap latent code with list"
-        latent, noise = self.styles_and_noise_forward(styles, noise, inject_index, truncation,
-                                                      truncation_latent, input_is_latent,
-                                                      randomize_noise)
-        latent = _lib.as_f32c(latent)
+        if prepared is not None:
+            latent, noise = prepared[0], prepared[1]
+        else:
+            latent, noise = self.styles_and_noise_forward(styles, noise, inject_index, truncation,
+                                                          truncation_latent, input_is_latent,
+                                                          randomize_noise)
+            latent = _lib.as_f32c(latent)
         x = _nhwc(features)
         out = self.conv1.forward_nhwc(x, latent[:, 0], noise[0])
         skip = self.to_rgb1.forward_nhwc(out, latent[:, 1], rgbd_in)
@@ -676,6 +717,13 @@ class Generator(nn.Module):
 class G_pred_latents(Generator):
     """Dict-returning generator the E3DGE runners call — stylesdf_model.py:1023-1172."""
 
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
+
     def forward(self, styles, cam_poses, focals, near=0.88, far=1.12, return_latents=False,
                 inject_index=None, truncation=1, truncation_latent=None, input_is_latent=False,
                 noise=None, randomize_noise=True, return_sdf=False, return_xyz=False,
@@ -695,26 +743,50 @@ class G_pred_latents(Generator):
             encoder_latent = styles[0]
         renderer_latent = self.styles_and_noise_forward([encoder_latent], inject_index, truncation,
                                                         truncation_latent, input_is_latent)
-        render_out = self.renderer(cam_poses, focals, near, far, styles=renderer_latent[0],
-                                   return_eikonal=return_eikonal, return_mesh=return_mesh,
-                                   mesh_with_shading=mesh_with_shading, sample_mode=sample_mode,
-                                   geometry_sample=geometry_sample,
-                                   return_surface_eikonal=return_surface_eikonal,
-                                   sample_without_grad=sample_without_grad, **kwargs)
-        render_out["styles"] = renderer_latent[0]
-        if renderer_only:
-            return render_out
-        if (self.full_pipeline or sample_with_decoder) and not sample_with_renderer:
-            if decoder_latent is None:
-                decoder_latent = renderer_latent
-            elif not isinstance(decoder_latent, list):
-                decoder_latent = [decoder_latent]
-            gen_imgs, decoder_latent = self.decoder(
-                render_out["features"], decoder_latent,
-                transform=cam_poses if project_noise else None, return_latents=return_latents,
-                inject_index=inject_index, truncation=truncation,
-                truncation_latent=truncation_latent, noise=noise, input_is_latent=input_is_latent,
-                randomize_noise=randomize_noise, mesh_path=mesh_path, conditions=conditions)
-            render_out["gen_imgs"] = gen_imgs
-            render_out["decoder_latent"] = decoder_latent
+        # Inference: the decoder's latent-only work (styles, demodulation, noise maps: ~25 tiny launches)
+        # goes to a side stream and runs under the render kernel instead of after it.
+        runs_decoder = (self.full_pipeline or sample_with_decoder) and not sample_with_renderer and not renderer_only
+        prepared = None
+        if (runs_decoder and not torch.is_grad_enabled() and renderer_latent[0].is_cuda
+                and not (sample_mode or project_noise)):
+            dl = renderer_latent if decoder_latent is None else (
+                decoder_latent if isinstance(decoder_latent, list) else [decoder_latent])
+            main = torch.cuda.current_stream()
+            side = self._side_stream(renderer_latent[0].device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                prepared = self.decoder.prepare(dl, renderer_latent[0].shape[0], noise, inject_index, truncation,
+                                                truncation_latent, input_is_latent, randomize_noise)
+            for t in prepared[2]:
+                t.record_stream(main)
+        try:
+            render_out = self.renderer(cam_poses, focals, near, far, styles=renderer_latent[0],
+                                       return_eikonal=return_eikonal, return_mesh=return_mesh,
+                                       mesh_with_shading=mesh_with_shading, sample_mode=sample_mode,
+                                       geometry_sample=geometry_sample,
+                                       return_surface_eikonal=return_surface_eikonal,
+                                       sample_without_grad=sample_without_grad, **kwargs)
+            render_out["styles"] = renderer_latent[0]
+            if renderer_only:
+                return render_out
+            if (self.full_pipeline or sample_with_decoder) and not sample_with_renderer:
+                if decoder_latent is None:
+                    decoder_latent = renderer_latent
+                elif not isinstance(decoder_latent, list):
+                    decoder_latent = [decoder_latent]
+                if prepared is not None:
+                    torch.cuda.current_stream().wait_stream(self._side_stream(render_out["features"].device))
+                gen_imgs, decoder_latent = self.decoder(
+                    render_out["features"], decoder_latent,
+                    transform=cam_poses if project_noise else None, return_latents=return_latents,
+                    inject_index=inject_index, truncation=truncation,
+                    truncation_latent=truncation_latent, noise=noise, input_is_latent=input_is_latent,
+                    randomize_noise=randomize_noise, mesh_path=mesh_path, conditions=conditions,
+                    prepared=prepared)
+                render_out["gen_imgs"] = gen_imgs
+                render_out["decoder_latent"] = decoder_latent
+        finally:
+            if prepared is not None:  # never leave a half-consumed prefetch behind (exceptions, early returns)
+                for conv, _ in self.decoder._layer_latents():
+                    conv._prefetched = None
         return render_out

@@ -1,0 +1,10 @@
+#!/bin/bash
+# side-stream decoder prepare + 8-lanes-per-pixel ToRGB
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8) > gpurun_out/r23_pytest.log
+for i in 1 2; do
+  (timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1) >> gpurun_out/r23_bench.json
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r23_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+tail -n 6 gpurun_out/r23_pytest.log; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r23_bench.json; grep -o '"e2e": {"value": [0-9.]*' gpurun_out/r23_bench.json
+python profiles/summarize_ncu.py launches gpurun_out/r23_launches.csv > gpurun_out/r23_launches.txt; head -22 gpurun_out/r23_launches.txt
