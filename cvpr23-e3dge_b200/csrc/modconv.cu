@@ -20,6 +20,7 @@
 //   * CUDA cores (this file): exact-fp32 FFMA implicit GEMM for every other shape, and the
 //     numerical baseline the tensor-core path is tested against.
 #include "modconv.cuh"
+#include "tcgen05.cuh"
 
 namespace e3 {
 
@@ -353,6 +354,11 @@ struct UpBlurArgs {
   int64_t noise_bstride;
   const float* noise_w;
   const float* act_bias;  // NULL: bare modulated conv
+  // inference fusion: when xs_hi is set, y is not written; the epilogue stores the NEXT plain conv's
+  // tensor-core operands xs = out * next_s[b,:] as bf16 hi / lo ([B,2H,2W,cout] each) instead
+  const float* next_s;
+  __nv_bfloat16* xs_hi;
+  __nv_bfloat16* xs_lo;
 };
 
 // weight of T row r (0..6, relative to 2y-1) in output row 2y+k (k = 0..3): kb[r - k], kb = [1,3,3,1]/4
@@ -416,6 +422,8 @@ __global__ void __launch_bounds__(256) upconv_blur_act_kernel(const __grid_const
     const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);
     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!linear) bv = *reinterpret_cast<const float4*>(a.act_bias + o);
+    float4 ns = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.xs_hi) ns = *reinterpret_cast<const float4*>(a.next_s + (size_t)b * a.cout + o);
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
@@ -431,8 +439,17 @@ __global__ void __launch_bounds__(256) upconv_blur_act_kernel(const __grid_const
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) v[qq] = (v[qq] > 0.f ? v[qq] : 0.2f * v[qq]) * kSqrt2;
         }
-        *reinterpret_cast<float4*>(a.y + (((size_t)b * OH + Y) * OW + X) * a.cout + o) =
-            make_float4(v[0], v[1], v[2], v[3]);
+        const size_t at = (((size_t)b * OH + Y) * OW + X) * a.cout + o;
+        if (a.xs_hi) {  // same arithmetic as modulate_split_kernel on the stored fp32 value
+          const float m[4] = {v[0] * ns.x, v[1] * ns.y, v[2] * ns.z, v[3] * ns.w};
+          __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) tc::split_bf16(m[qq], h[qq], l[qq]);
+          *reinterpret_cast<uint2*>(a.xs_hi + at) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(a.xs_lo + at) = *reinterpret_cast<const uint2*>(l);
+        } else {
+          *reinterpret_cast<float4*>(a.y + at) = make_float4(v[0], v[1], v[2], v[3]);
+        }
       }
   }
 }
@@ -683,16 +700,14 @@ extern "C" int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const 
   return E3_OK;
 }
 
-extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, const float* s,
-                                        const float* d, const float* noise,
-                                        int64_t noise_batch_stride, const float* noise_w,
-                                        const float* act_bias, float* y, int batch, int h, int w,
-                                        int cin, int cout, void* scratch, size_t scratch_bytes,
-                                        uint32_t flags, void* stream) {
+static int up_fwd_impl(const float* x, const void* wpacked, const float* s, const float* d, const float* noise,
+                       int64_t noise_batch_stride, const float* noise_w, const float* act_bias, float* y,
+                       const float* next_s, void* xs_hi, void* xs_lo, int batch, int h, int w, int cin,
+                       int cout, void* scratch, size_t scratch_bytes, uint32_t flags, void* stream) {
   int rc = check_conv_shapes("e3_styled_conv3x3_up_fwd", batch, h, w, cin, cout);
   if (rc) return rc;
   if (batch == 0) return E3_OK;
-  E3_REQUIRE(x && wpacked && s && d && y, E3_ERR_BAD_ARG, "e3_styled_conv3x3_up_fwd: null argument");
+  E3_REQUIRE(x && wpacked && s && d && (y || xs_hi), E3_ERR_BAD_ARG, "e3_styled_conv3x3_up_fwd: null argument");
   E3_REQUIRE(!act_bias || (noise && noise_w), E3_ERR_BAD_ARG,
              "e3_styled_conv3x3_up_fwd: noise and noise_w are required unless act_bias is NULL");
   const size_t need = e3_styled_conv_scratch_bytes(batch, h, w, cin, cout, 1);
@@ -705,6 +720,8 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
   const bool tcore = !(flags & E3_CONV_FP32_CUDA_CORES) && tc_upconv_supported(batch, h, w, cin, cout);
   E3_REQUIRE(tcore || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
              "e3_styled_conv3x3_up_fwd: E3_CONV_TENSOR_CORES requested for an unsupported shape");
+  E3_REQUIRE(tcore || !xs_hi, E3_ERR_UNSUPPORTED,
+             "e3_styled_conv3x3_up_fwd_split: the fused operand split exists on the tensor-core path only");
   if (tcore) {
     // four parity-phase convolutions accumulate the transposed conv in TMEM -> T, then blur + epilogue
     size_t t_bytes = tc_upconv_t_bytes(batch, h, w, cout);
@@ -719,6 +736,7 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
     UpBlurArgs u{};
     u.t = t_out, u.y = y, u.B = batch, u.H = h, u.W = w, u.cout = cout;
     u.d = d, u.noise = noise, u.noise_bstride = noise_batch_stride, u.noise_w = noise_w, u.act_bias = act_bias;
+    u.next_s = next_s, u.xs_hi = static_cast<__nv_bfloat16*>(xs_hi), u.xs_lo = static_cast<__nv_bfloat16*>(xs_lo);
     const int64_t total = (int64_t)batch * ((h + 1) / 2) * ((w + 1) / 2) * (cout / 4);
     upconv_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(u);
     E3_CUDA(cudaGetLastError());
@@ -738,6 +756,56 @@ extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, con
   col2im_blur_act_kernel<<<grid_cap((total + 255) / 256), 256, 0, as_stream(stream)>>>(c);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
+}
+
+extern "C" int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, const float* s,
+                                        const float* d, const float* noise,
+                                        int64_t noise_batch_stride, const float* noise_w,
+                                        const float* act_bias, float* y, int batch, int h, int w,
+                                        int cin, int cout, void* scratch, size_t scratch_bytes,
+                                        uint32_t flags, void* stream) {
+  E3_REQUIRE(y || batch == 0, E3_ERR_BAD_ARG, "e3_styled_conv3x3_up_fwd: null argument");
+  return up_fwd_impl(x, wpacked, s, d, noise, noise_batch_stride, noise_w, act_bias, y, nullptr, nullptr, nullptr,
+                     batch, h, w, cin, cout, scratch, scratch_bytes, flags, stream);
+}
+
+extern "C" int e3_styled_conv_pair_fusable(int batch, int h, int w, int cin, int cout, uint32_t flags) {
+  if (flags & E3_CONV_FP32_CUDA_CORES) return 0;
+  return tc_upconv_supported(batch, h, w, cin, cout) && tc_conv_supported(batch, 2 * h, 2 * w, cout, cout) ? 1 : 0;
+}
+
+extern "C" int e3_styled_conv3x3_up_fwd_split(const float* x, const void* wpacked, const float* s,
+                                              const float* d, const float* noise,
+                                              int64_t noise_batch_stride, const float* noise_w,
+                                              const float* act_bias, const float* next_s, void* xs_hi,
+                                              void* xs_lo, int batch, int h, int w, int cin, int cout,
+                                              void* scratch, size_t scratch_bytes, uint32_t flags,
+                                              void* stream) {
+  E3_REQUIRE((next_s && xs_hi && xs_lo) || batch == 0, E3_ERR_BAD_ARG,
+             "e3_styled_conv3x3_up_fwd_split: null argument");
+  return up_fwd_impl(x, wpacked, s, d, noise, noise_batch_stride, noise_w, act_bias, nullptr, next_s, xs_hi, xs_lo,
+                     batch, h, w, cin, cout, scratch, scratch_bytes, flags, stream);
+}
+
+extern "C" int e3_styled_conv3x3_fwd_presplit(const void* xs_hi, const void* xs_lo, const void* wpacked,
+                                              const float* d, const float* noise,
+                                              int64_t noise_batch_stride, const float* noise_w,
+                                              const float* act_bias, float* y, int batch, int h, int w,
+                                              int cin, int cout, uint32_t flags, void* stream) {
+  int rc = check_conv_shapes("e3_styled_conv3x3_fwd_presplit", batch, h, w, cin, cout);
+  if (rc) return rc;
+  if (batch == 0) return E3_OK;
+  E3_REQUIRE(xs_hi && xs_lo && wpacked && d && y, E3_ERR_BAD_ARG, "e3_styled_conv3x3_fwd_presplit: null argument");
+  E3_REQUIRE(!act_bias || (noise && noise_w), E3_ERR_BAD_ARG,
+             "e3_styled_conv3x3_fwd_presplit: noise and noise_w are required unless act_bias is NULL");
+  E3_REQUIRE(use_tensor_cores(flags, batch, h, w, cin, cout), E3_ERR_UNSUPPORTED,
+             "e3_styled_conv3x3_fwd_presplit: pre-split operands exist on the tensor-core path only");
+  ConvGemmArgs a{};
+  a.out = y;
+  a.B = batch, a.H = h, a.W = w, a.Cin = cin, a.N = cout;
+  a.mode = act_bias ? 1 : 2, a.d = d, a.noise = noise, a.noise_bstride = noise_batch_stride;
+  a.noise_w = noise_w, a.act_bias = act_bias;
+  return tc_conv_launch_presplit(a, 9, packed_bf16_part(wpacked, cout, cin), xs_hi, xs_lo, as_stream(stream));
 }
 
 extern "C" int e3_torgb_fwd(const float* x, const float* weight, const float* s, const float* bias,

@@ -94,6 +94,12 @@ _PROTOTYPES = {
     "e3_styled_conv3x3_up_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, c_int,
                                          c_int, c_int, c_int, c_int, _fp, c_size_t, c_uint32, _fp]),
     "e3_styled_conv_scratch_bytes": (c_size_t, [c_int] * 6),
+    "e3_styled_conv_pair_fusable": (c_int, [c_int] * 5 + [c_uint32]),
+    "e3_styled_conv3x3_up_fwd_split": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, _fp,
+                                               c_int, c_int, c_int, c_int, c_int, _fp, c_size_t, c_uint32,
+                                               _fp]),
+    "e3_styled_conv3x3_fwd_presplit": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, c_int,
+                                               c_int, c_int, c_int, c_int, c_uint32, _fp]),
     "e3_styled_conv_bwd_scratch_bytes": (c_size_t, [c_int] * 6),
     "e3_styled_conv3x3_bwd": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, _fp,
                                       c_int, c_int, c_int, c_int, c_int, c_int, _fp, c_size_t, c_uint32,
@@ -139,7 +145,8 @@ KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
                     "e3_siren_points_bwd": 3, "e3_film_bwd": 1, "e3_fused_bias_act": 1, "e3_upfirdn2d": 1,
                     "e3_modconv_weight_sq": 1, "e3_modconv_styles": 2, "e3_nchw_to_nhwc": 1,
                     "e3_nhwc_to_nchw": 1, "e3_conv_pack_weight": 1, "e3_styled_conv3x3_fwd": 2,
-                    "e3_styled_conv3x3_up_fwd": 3, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
+                    "e3_styled_conv3x3_up_fwd": 3, "e3_styled_conv3x3_up_fwd_split": 3,
+                    "e3_styled_conv3x3_fwd_presplit": 1, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
                     "e3_torgb_bwd": 2, "e3_modconv_styles_bwd": 1,
                     "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1}
 launch_count = 0

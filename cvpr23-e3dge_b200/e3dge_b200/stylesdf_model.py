@@ -10,6 +10,7 @@ checkpoints load unchanged and the runners can call `generator(...)` as they do 
 Inside `Decoder.forward` activations stay channels-last fp32 between layers; the NCHW
 contract of the reference holds at the module boundaries.
 """
+import ctypes
 import math
 import random
 
@@ -401,6 +402,63 @@ def _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias, want_saved=Fals
     return y
 
 
+FUSE_CONV_PAIRS = True  # inference: hand the up-conv's output to the next conv as bf16 hi / lo operands
+
+
+def _pair_fusable(up, plain, x):
+    """Can e3_styled_conv3x3_up_fwd_split / _fwd_presplit run this (upsampling, plain) StyledConv pair?"""
+    if not FUSE_CONV_PAIRS:
+        return False
+    cu, cp = up.conv, plain.conv
+    if not (cu.upsample and not cp.upsample and cp.in_channel == cu.out_channel == cp.out_channel
+            and cu.kernel_size == cp.kernel_size == 3 and cu.demodulate and cp.demodulate):
+        return False
+    if cu.backend == "fp32" or cp.backend == "fp32":
+        return False
+    b, h, w, cin = x.shape
+    return bool(_lib.load().e3_styled_conv_pair_fusable(b, h, w, cin, cu.out_channel, CONV_BACKENDS["auto"]))
+
+
+def _styled_conv_pair_nhwc(up, plain, x, lat_up, lat_plain, noise_up, noise_plain):
+    """Inference only: StyledConv(upsample) -> StyledConv of one resolution step with the intermediate
+    activation handed over as the second conv's bf16 hi / lo operands (include/e3dge_b200.h)."""
+    lib = _lib.load()
+    cu, cp = up.conv, plain.conv
+    b, h, w, cin = x.shape
+    c = cu.out_channel
+    oh, ow = 2 * h, 2 * w
+    x = _lib.as_f32c(x.detach())
+    s1, d1 = cu.styles(lat_up.detach())
+    s2, d2 = cp.styles(lat_plain.detach())
+    wp1, _ = cu._packed.get(cu.weight, 1)
+    wp2, _ = cp._packed.get(cp.weight, 0)
+
+    def noise_of(n):
+        n = torch.empty(b, 1, oh, ow, device=x.device).normal_() if n is None else _lib.as_f32c(n)
+        if n.numel() == b * oh * ow and b > 1:
+            return n, oh * ow
+        if n.numel() != oh * ow:
+            raise RuntimeError(f"noise of {tuple(n.shape)} does not match a {oh}x{ow} layer")
+        return n, 0
+    n1, st1 = noise_of(noise_up)
+    n2, st2 = noise_of(noise_plain)
+    xs = torch.empty(2, b, oh, ow, c, device=x.device, dtype=torch.bfloat16)
+    nbytes = lib.e3_styled_conv_scratch_bytes(b, h, w, cin, c, 1)
+    scratch = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    f32 = lambda t: _lib.ptr(_lib.as_f32c(t.detach()))
+    _lib.check(lib.e3_styled_conv3x3_up_fwd_split(
+        _lib.ptr(x), _lib.ptr(wp1), _lib.ptr(s1), _lib.ptr(d1), _lib.ptr(n1), st1, f32(up.noise.weight),
+        f32(up.activate.bias), _lib.ptr(s2), vp(xs[0]), vp(xs[1]), b, h, w, cin, c, _lib.ptr(scratch), nbytes,
+        CONV_BACKENDS[cu.backend], _lib.cur_stream()), "e3_styled_conv3x3_up_fwd_split")
+    y = torch.empty(b, oh, ow, c, device=x.device, dtype=torch.float32)
+    _lib.check(lib.e3_styled_conv3x3_fwd_presplit(
+        vp(xs[0]), vp(xs[1]), _lib.ptr(wp2), _lib.ptr(d2), _lib.ptr(n2), st2, f32(plain.noise.weight),
+        f32(plain.activate.bias), _lib.ptr(y), b, oh, ow, c, c, CONV_BACKENDS[cp.backend], _lib.cur_stream()),
+        "e3_styled_conv3x3_fwd_presplit")
+    return y
+
+
 def _torgb_nhwc(conv, x, latent, bias, skip, upsample_skip, want_saved=False):
     lib = _lib.load()
     b, h, w, cin = x.shape
@@ -611,8 +669,11 @@ class Decoder(nn.Module):
         i = 1
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2],
                                                         noise[1::2], noise[2::2], self.to_rgbs):
-            out = conv1.forward_nhwc(out, latent[:, i], noise1)
-            out = conv2.forward_nhwc(out, latent[:, i + 1], noise2)
+            if not _wants_grad(out, latent) and _pair_fusable(conv1, conv2, out):
+                out = _styled_conv_pair_nhwc(conv1, conv2, out, latent[:, i], latent[:, i + 1], noise1, noise2)
+            else:
+                out = conv1.forward_nhwc(out, latent[:, i], noise1)
+                out = conv2.forward_nhwc(out, latent[:, i + 1], noise2)
             skip = to_rgb.forward_nhwc(out, latent[:, i + 2], skip)
             i += 2
         return skip, (latent if return_latents else None)

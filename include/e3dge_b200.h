@@ -297,6 +297,25 @@ int e3_styled_conv3x3_up_fwd(const float* x, const void* wpacked, const float* s
                              uint32_t flags, void* stream);
 size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout, int upsample);
 
+/* Inference fusion of one resolution step of Decoder.forward (stylesdf_model.py:783-790: an upsampling
+ * StyledConv followed by a plain one of the same width).  Nothing but the next conv reads the first
+ * layer's output, so ..._up_fwd_split writes, instead of y, the next conv's tensor-core operands
+ * xs = y * next_s[b,:] as bf16 hi / lo ([B,2H,2W,cout] each; bit-identical to what e3_styled_conv3x3_fwd
+ * derives from y), and ..._fwd_presplit is e3_styled_conv3x3_fwd on such operands (cin = the first
+ * layer's cout).  Tensor-core path only: e3_styled_conv_pair_fusable says whether the shapes allow it
+ * (1) or the caller runs the two layers separately (0).  Scratch as for e3_styled_conv3x3_up_fwd. */
+int e3_styled_conv_pair_fusable(int batch, int h, int w, int cin, int cout, uint32_t flags);
+int e3_styled_conv3x3_up_fwd_split(const float* x, const void* wpacked, const float* s,
+                                   const float* d, const float* noise,
+                                   int64_t noise_batch_stride, const float* noise_w,
+                                   const float* act_bias, const float* next_s, void* xs_hi,
+                                   void* xs_lo, int batch, int h, int w, int cin, int cout,
+                                   void* scratch, size_t scratch_bytes, uint32_t flags, void* stream);
+int e3_styled_conv3x3_fwd_presplit(const void* xs_hi, const void* xs_lo, const void* wpacked,
+                                   const float* d, const float* noise, int64_t noise_batch_stride,
+                                   const float* noise_w, const float* act_bias, float* y, int batch,
+                                   int h, int w, int cin, int cout, uint32_t flags, void* stream);
+
 /* ToRGB forward (stylesdf_model.py:531-541, Upsample :96-119): 1x1 modulated conv without
  * demodulation + bias + (optionally FIR-upsampled) skip.
  * x [B,H,W,cin] NHWC; weight [3,cin]; skip NULL, or [B,3,H/2,W/2] NCHW when

@@ -297,6 +297,34 @@ def test_tensor_core_conv_vs_fp32_path_and_oracle(cin, cout, hw, batch, up):
         assert rel_linf(y_tc.cpu(), y_ref) < 1e-4
 
 
+def test_fused_conv_pair_and_side_stream_prepare_are_bit_identical_to_the_layerwise_pass(monkeypatch):
+    """Inference runs each (upsampling conv, plain conv) step through e3_styled_conv3x3_up_fwd_split /
+    _fwd_presplit (no fp32 activation between the two) and computes styles / noise on a side stream; both
+    must reproduce the layer-by-layer decoder exactly, with fixed and with fresh noise."""
+    import e3dge_b200.stylesdf_model as M
+    size, res, seed = 256, 64, 77
+    G, sd = _build(size, res, seed, "default")
+    inp = _cuda(P.make_inputs(seed, 2, decoder_layout(size, res), res))
+    args = ([inp["w"], inp["w_dec"]], inp["cam_poses"], inp["focal"], inp["near"], inp["far"])
+    feats = torch.randn(2, 256, res, res, device="cuda") * 0.3
+    with torch.no_grad():
+        fused, _ = G.decoder(feats, [inp["w_dec"]], input_is_latent=True, randomize_noise=False)
+        torch.manual_seed(5)
+        full_fused = G(*args, input_is_latent=True, randomize_noise=True)["gen_imgs"]
+        monkeypatch.setattr(M, "FUSE_CONV_PAIRS", False)
+        plain, _ = G.decoder(feats, [inp["w_dec"]], input_is_latent=True, randomize_noise=False)
+        torch.manual_seed(5)
+        full_plain = G(*args, input_is_latent=True, randomize_noise=True)["gen_imgs"]
+    assert torch.equal(fused, plain)
+    assert torch.equal(full_fused, full_plain)
+    # the same pass with gradients enabled takes the layer-wise autograd path (no side stream, no fusion)
+    monkeypatch.setattr(M, "FUSE_CONV_PAIRS", True)
+    w = inp["w_dec"].clone().requires_grad_(True)
+    torch.manual_seed(5)
+    img = G([inp["w"], w], *args[1:], input_is_latent=True, randomize_noise=True)["gen_imgs"]
+    assert rel_linf(img.detach().cpu(), full_fused.cpu()) < 1e-5
+
+
 def test_tensor_core_request_on_unsupported_shape_fails_loudly():
     from e3dge_b200.stylesdf_model import StyledConv
     m = StyledConv(16, 24, 3, 512).cuda()
