@@ -117,7 +117,9 @@ __global__ void siren_pack_kernel(e3_siren_weights w, float* __restrict__ packed
   packed[idx] = v;
 }
 
-// gamma/beta of all 9 FiLM layers of one image: one warp per output row, lanes over k.
+// gamma/beta of all 9 FiLM layers of one image: one warp per output row, lanes over k.  Latency-bound
+// (4.7 MB of weights, 9 MFLOP): blockIdx.y splits the 256 rows into 8 chunks and a warp requests its
+// four rows' 64 coalesced loads at once.
 __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ packed,
                                                    const float* __restrict__ styles,
                                                    int styles_per_image,
@@ -132,12 +134,14 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ pac
   const float* gw = packed + OFF_GAMMA_W + (size_t)l * SW * SW;
   const float* bw = packed + OFF_BETA_W + (size_t)l * SW * SW;
   float* out = film + ((size_t)b * 9 + l) * FILM_ROWS * SW;
-  for (int n = warp; n < SW; n += 8) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int n = blockIdx.y * 32 + warp * 4 + r;
     float g = 0.f, be = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      g = fmaf(gw[n * SW + lane + 32 * i], s[i], g);
-      be = fmaf(bw[n * SW + lane + 32 * i], s[i], be);
+      g = fmaf(__ldg(gw + n * SW + lane + 32 * i), s[i], g);
+      be = fmaf(__ldg(bw + n * SW + lane + 32 * i), s[i], be);
     }
     g = warp_sum(g);
     be = warp_sum(be);
@@ -640,8 +644,8 @@ extern "C" int e3_film_fwd(const void* packed, const float* styles, int batch, i
              "e3_film_fwd: styles_per_image must be 1 (w) or 9 (w+), got %d", styles_per_image);
   if (batch == 0) return E3_OK;  // empty batches carry null data pointers
   E3_REQUIRE(packed && styles && film, E3_ERR_BAD_ARG, "e3_film_fwd: null argument");
-  film_kernel<<<batch * 9, 256, 0, as_stream(stream)>>>(static_cast<const float*>(packed), styles,
-                                                       styles_per_image, film);
+  film_kernel<<<dim3(batch * 9, SW / 32), 256, 0, as_stream(stream)>>>(static_cast<const float*>(packed), styles,
+                                                                      styles_per_image, film);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
 }

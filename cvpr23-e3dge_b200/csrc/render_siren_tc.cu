@@ -545,6 +545,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       float* stash = (STASH && !dummy) ? a.stash + (size_t)tile * STASH_FLOATS_PER_TILE + m : nullptr;
       const bool tr = a.trace && blockIdx.x == 0 && slot == 1 && tid == 64;
       if (tr) a.trace[0] = clock64();
+      if (a.trace && blockIdx.x == 0 && slot == 2 && tid == 64) a.trace[68] = clock64();  // next tile's layer 0 starts
 
       // ---- layer 0 (K = 3) on the CUDA cores: h0 = sin(gamma*(W0 x) + beta'), 4 blocks ----
 #pragma unroll 1
@@ -871,7 +872,9 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         sm.rgb_part[hw][1][m] = c1;
         sm.rgb_part[hw][2][m] = c2;
         tc::fence_before_thread_sync();
+        if (tr) a.trace[66] = clock64();
         compute_sync();
+        if (tr) a.trace[67] = clock64();
 
         if (MODE == 0) {
           if (a.out.raw_rgb && hw == 0 && valid) {

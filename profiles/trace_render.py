@@ -26,7 +26,8 @@ for l in range(8):
     mw = [rel(t[128 + l * 8 + kb]) for kb in range(4)]
     mi = [rel(t[256 + l * 16 + kb * 4 + 3]) for kb in range(4)]
     print(f"L{l}  {comp[0]}  {comp[1:]}  ||  G{l}: {mw}  {mi}")
-print("view-layer d_ready seen:", rel(t[64]), " tile end:", rel(t[65]))
+print("view-layer d_ready seen:", rel(t[64]), " view epilogue done (this warp):", rel(t[66]), " all warps:", rel(t[67]),
+      " tile end:", rel(t[65]), " next tile's layer 0 starts:", rel(t[68]))
 # inside layer 3 (warp 2 lane 0): per 64-channel block, cycles since the layer's d_ready was seen
 base = t[3 * 8]
 if t[384]:
