@@ -450,18 +450,29 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       const size_t samp0 = ((size_t)b * HW + unit0) * S;
       const bool valid = m < n_valid;
       const int r = valid ? m / S : 0, s = valid ? m - r * S : 0;
+      float pre_film[3], pre_w0[2];
+      bool film_rows_pending;
 
       {  // FiLM table of this image -> shared memory (rows gamma, beta'); the previous tile's view-layer
          // epilogue parked W_dir / W_rgb in the rows of layers 0..2, so those come back every tile
         const float* f = a.in.film + (size_t)b * 9 * FILM_ROWS * SW;
         const int n_layers = (b != cur_b) ? 9 : (a.with_view ? 3 : 0);
-        for (int i = ct; i < n_layers * 2 * SW; i += TC_COMPUTE) {
+        for (int i = ct + 3 * 2 * SW; i < n_layers * 2 * SW; i += TC_COMPUTE) {  // layers 3..8: new image only
           const int l = i / (2 * SW), row = (i / SW) & 1, n = i % SW;
           sm.film[l][row][n] = f[(l * FILM_ROWS + (row ? 2 : 0)) * SW + n];
         }
+        // rows of layers 0..2 (3 values per thread) and the layer-0 weights [3][256] (they live in the
+        // rgb_part array, which is only used at the end of a tile): requested here, stored after the
+        // geometry below so that the two latencies overlap
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = ct + k * TC_COMPUTE, l = i / (2 * SW), row = (i / SW) & 1, n = i % SW;
+          pre_film[k] = n_layers ? __ldg(f + (l * FILM_ROWS + (row ? 2 : 0)) * SW + n) : 0.f;
+        }
+        pre_w0[0] = __ldg(pk + OFF_W0N + ct);
+        pre_w0[1] = ct < SW ? __ldg(pk + OFF_W0N + TC_COMPUTE + ct) : 0.f;
+        film_rows_pending = n_layers != 0;
         cur_b = b;
-        // layer-0 weights [3][256] live in the rgb_part array, which is only used at the end of a tile
-        for (int i = ct; i < 3 * SW; i += TC_COMPUTE) w0s[i] = __ldg(pk + OFF_W0N + i);
       }
 
       // ---- per-row geometry, recomputed by both column halves ----
@@ -531,6 +542,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         }
       }
 
+      if (film_rows_pending) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) (&sm.film[0][0][0])[ct + k * TC_COMPUTE] = pre_film[k];
+      }
+      w0s[ct] = pre_w0[0];
+      if (ct < SW) w0s[TC_COMPUTE + ct] = pre_w0[1];
       compute_sync();  // FiLM table visible; the previous tile's readers of shared arrays are done
 
       // rendering.return_feats: hidden states after 0-based layers 0,2,4,6 (volume_renderer.py:179-180)
@@ -784,10 +801,21 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         float* fbuf = reinterpret_cast<float*>(sm.a_hi);  // [256][128] fp32 over a_hi + a_lo
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         f32x2 C0 = pk2(0.f, 0.f), C1 = C0, C2 = C0;  // packed rgb-head sums (even, odd channels)
+        // the TMEM read of block j+1 is in flight while block j is processed (this epilogue is on the
+        // tile's critical path: nothing else runs on the SM)
+        uint32_t nxt[16];
+        if (EPI & 1) tc::tmem_ld_32x16_issue(dsrc, nxt);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           float acc[16];
-          tc::tmem_ld_32x16(dsrc + j * 64, acc);
+          if (EPI & 1) {
+            tc::tmem_ld_wait16(nxt);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(nxt[i]);
+            if (j < 3) tc::tmem_ld_32x16_issue(dsrc + (j + 1) * 64, nxt);
+          } else {
+            tc::tmem_ld_32x16(dsrc + j * 64, acc);
+          }
           const int nb = j * 64 + hw * 16;
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -877,23 +905,17 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         if (tr) a.trace[67] = clock64();
 
         if (MODE == 0) {
-          if (a.out.raw_rgb && hw == 0 && valid) {
-            float* o = a.out.raw_rgb + (samp0 + m) * 3;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              o[c] = (sm.rgb_part[0][c][m] + sm.rgb_part[1][c][m]) + (sm.rgb_part[2][c][m] + sm.rgb_part[3][c][m]) +
-                     pk[OFF_HEADB + 1 + c];
-          }
-          if (a.out.thumb_rgb && ct < 3 * n_units) {
-            const int c = ct / n_units, rr = ct - c * n_units;
-            float accum = 0.f;
-            for (int si = 0; si < S; ++si) {
-              const int mm = rr * S + si;
-              const float raw = (sm.rgb_part[0][c][mm] + sm.rgb_part[1][c][mm]) +
-                                (sm.rgb_part[2][c][mm] + sm.rgb_part[3][c][mm]) + pk[OFF_HEADB + 1 + c];
-              accum = fmaf(sm.wgt[mm], sigmoid_acc(raw), accum);
+          // rgb head: one thread per (colour, sample) closes the four column-quarter partial sums, writes the
+          // raw value and leaves w * sigmoid(raw) in place for the per-ray sums below (the 24 sigmoids of a
+          // ray used to run one after the other in a single thread)
+          if (ct < 3 * TCM) {
+            const int c = ct >> 7, mm = ct & (TCM - 1);
+            const float raw = (sm.rgb_part[0][c][mm] + sm.rgb_part[1][c][mm]) +
+                              (sm.rgb_part[2][c][mm] + sm.rgb_part[3][c][mm]) + pk[OFF_HEADB + 1 + c];
+            if (mm < n_valid) {
+              if (a.out.raw_rgb) a.out.raw_rgb[(samp0 + mm) * 3 + c] = raw;
+              sm.rgb_part[0][c][mm] = __fmul_rn(sm.wgt[mm], sigmoid_acc(raw));
             }
-            a.out.thumb_rgb[((size_t)b * 3 + c) * HW + unit0 + rr] = -1.f + 2.f * accum;
           }
           if (a.out.features) {
             const int n = ct & (SW - 1);  // one output channel per thread pair: even / odd rays
@@ -909,6 +931,15 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               }
               if (si < S) acc0 += row[(rr * S + si) ^ sw];
               o[rr] = acc0 + acc1;
+            }
+          }
+          if (a.out.thumb_rgb) {
+            compute_sync();
+            if (ct < 3 * n_units) {
+              const int c = ct / n_units, rr = ct - c * n_units;
+              float accum = 0.f;
+              for (int si = 0; si < S; ++si) accum = __fadd_rn(accum, sm.rgb_part[0][c][rr * S + si]);
+              a.out.thumb_rgb[((size_t)b * 3 + c) * HW + unit0 + rr] = -1.f + 2.f * accum;
             }
           }
         } else if (a.p_rgb && hw == 0 && valid) {
