@@ -78,27 +78,12 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// The release form above costs ~1.5k cycles (a cluster-scope fence).  The forwarder thread of the paired
-// render kernel has nothing of its own to publish: the data are shared-memory stores of OTHER threads
-// that already performed (proxy fence + CTA-scope release-arrive, acquired by this thread) and are read by
-// the tensor core of the SM that holds them.
+// Remote arrive without the release fence: `mbarrier.arrive.release.cluster` costs ~1.5k cycles (a
+// cluster-scope fence, measured on the epilogue's critical path).  In the paired render kernel the arriving
+// warp has already completed its shared-memory stores with a proxy fence, and they are read by the tensor
+// core of the SM that holds them.
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
 }
 // 2-D tensor-map load into THIS CTA's shared memory whose bytes are counted on a barrier that may
 // live in the pair's other CTA (`bar_cluster_addr` from map_to_cta)
@@ -228,17 +213,6 @@ __device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
                :
-               : "memory");
-}
-// two 32x8 loads, columns [c, c+8) and [c+32, c+40), into r[0..7] and r[8..15]
-__device__ __forceinline__ void tmem_ld_2x32x8_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr + 32)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
