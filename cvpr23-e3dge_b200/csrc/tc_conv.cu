@@ -33,8 +33,20 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+static int make_tensor_map_typed(CUtensorMap* tm, CUtensorMapDataType dtype, const void* base, int rank,
+                                 const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                 bool swizzle128);
 int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  return make_tensor_map_typed(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle128);
+}
+int make_tensor_map_f32(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  return make_tensor_map_typed(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle128);
+}
+static int make_tensor_map_typed(CUtensorMap* tm, CUtensorMapDataType dtype, const void* base, int rank,
+                                 const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                 bool swizzle128) {
   PFN_encodeTiled enc = get_encode_tiled();
   E3_REQUIRE(enc != nullptr, E3_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
   cuuint64_t gdim[5], gstr[5];
@@ -45,7 +57,7 @@ int make_tensor_map_bf16(CUtensorMap* tm, const void* base, int rank, const uint
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base),
                    gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -122,7 +134,13 @@ __global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = 128 * 128;            // one operand tile: 128 rows x 128 B
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+// Epilogue staging: each group of 4 epilogue warps (one per TMEM lane quarter) owns a 128-row x 32-column
+// fp32 buffer in the TMA 128B-swizzled layout; one thread of the group hands it to a TMA tensor store.
+// (Each thread storing its own row, 32 lanes x 16 B to 32 different lines per instruction, held the
+// epilogue at ~8k cycles per tile and stalled on the store queue; full-line TMA writes do not.)
+constexpr int TC_OUT_CHUNK_BYTES = TC_BM * 32 * 4;
+constexpr int TC_OUT_GROUPS = 2;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_OUT_GROUPS * TC_OUT_CHUNK_BYTES + 256 + 1024;
 constexpr int TC_EPI_WARPS = 8;  // two per TMEM lane quarter, each draining half of the tile's columns
 constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
 
@@ -139,10 +157,12 @@ template <int TAPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const __grid_constant__ ConvGemmArgs a, const __grid_constant__ TcTile t) {
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvGemmArgs a,
+               const __grid_constant__ TcTile t) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint8_t* out_stage = smem + TC_STAGES * TC_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_GROUPS * TC_OUT_CHUNK_BYTES);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* acc_full = empty + TC_STAGES;
   uint64_t* acc_empty = acc_full + TC_ACC_BUFS;
@@ -158,6 +178,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc::prefetch_tensormap(&tmA_lo);
     tc::prefetch_tensormap(&tmB_hi);
     tc::prefetch_tensormap(&tmB_lo);
+    tc::prefetch_tensormap(&tmOut);
 #pragma unroll
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -250,6 +271,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int m = q * 32 + lane;
     const int ix = m % t.bw, iy = (m / t.bw) % t.bh, ib = m / (t.bw * t.bh);
     const float nw = (a.mode == 1) ? a.noise_w[0] : 0.f;
+    uint8_t* obuf = out_stage + chalf * TC_OUT_CHUNK_BYTES;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int x0, y0, b0, n0;
@@ -259,7 +281,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const bool valid = b < a.B;
       const int p = y * a.W + x;
       const float nz = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
-      float* orow = a.out + (((size_t)(valid ? b : 0) * a.H + y) * a.W + x) * a.N + n0;
       mbar_wait(&acc_full[buf], use & 1);
       tc::fence_after_thread_sync();
       constexpr int kChunksPerWarp = TC_BN / 32 / (TC_EPI_WARPS / 4);
@@ -272,23 +293,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (!valid) continue;
         const int nb = n0 + chunk * 32;
-        if (a.mode == 1) {
+        if (valid && a.mode == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float tt = fmaf(v[j], a.d[(size_t)b * a.N + nb + j], nz) + a.act_bias[nb + j];
             v[j] = (tt > 0.f ? tt : 0.2f * tt) * 1.41421356237309515f;
           }
-        } else if (a.mode == 2) {
+        } else if (valid && a.mode == 2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= a.d[(size_t)b * a.N + nb + j];
         }
-        float4* dst = reinterpret_cast<float4*>(orow + chunk * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        // registers -> swizzled staging buffer of this warp group -> one TMA tensor store (rows of images
+        // past the batch are clipped by the tensor map)
+        tc::named_bar_sync(2 + chalf, 128);  // the group's previous store has finished reading the buffer
+        tc::stage_row32(obuf, m, v);
+        fence_proxy_async();
+        tc::named_bar_sync(2 + chalf, 128);
+        if (q == 0 && lane == 0) {
+          tc::tma_store_4d(&tmOut, obuf, nb, x0, y0, b0);
+          tc::tma_store_commit_and_wait_read();
+        }
       }
     }
+    if (q == 0 && lane == 0) tc::tma_store_wait_all();
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -350,10 +378,11 @@ __global__ void __launch_bounds__(256) modulate_split_padded_kernel(const float*
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                       const __grid_constant__ UpPhaseArgs a) {
+                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ UpPhaseArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint8_t* out_stage = smem + TC_STAGES * TC_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_GROUPS * TC_OUT_CHUNK_BYTES);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* acc_full = empty + TC_STAGES;
   uint64_t* acc_empty = acc_full + TC_ACC_BUFS;
@@ -370,6 +399,7 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     tc::prefetch_tensormap(&tmA_lo);
     tc::prefetch_tensormap(&tmB_hi);
     tc::prefetch_tensormap(&tmB_lo);
+    tc::prefetch_tensormap(&tmOut);
 #pragma unroll
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -472,14 +502,12 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    uint8_t* obuf = out_stage + chalf * TC_OUT_CHUNK_BYTES;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int p, m0, n0;
       tile_coords(tile, p, m0, n0);
       const uint32_t buf = it & 1, use = it >> 1;
-      const int m = m0 + row;
-      const bool valid = m < a.Mp;
-      float* orow = a.t_out + ((size_t)p * a.Mp + (valid ? m : 0)) * a.N + n0;
       mbar_wait(&acc_full[buf], use & 1);
       tc::fence_after_thread_sync();
       constexpr int kChunksPerWarp = TC_BN / 32 / (TC_EPI_WARPS / 4);
@@ -492,12 +520,18 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (!valid) continue;
-        float4* dst = reinterpret_cast<float4*>(orow + chunk * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        // staging buffer -> TMA tensor store into T[phase] (rows past Mp are clipped by the tensor map)
+        tc::named_bar_sync(2 + chalf, 128);
+        tc::stage_row32(obuf, row, v);
+        fence_proxy_async();
+        tc::named_bar_sync(2 + chalf, 128);
+        if (q == 0 && lane == 0) {
+          tc::tma_store_3d(&tmOut, obuf, n0 + chunk * 32, m0, p);
+          tc::tma_store_commit_and_wait_read();
+        }
       }
     }
+    if (q == 0 && lane == 0) tc::tma_store_wait_all();
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -553,13 +587,18 @@ int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, 
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
+  CUtensorMap tmOut;  // T as [phase][Mp][cout] fp32, box = 32 channels x 128 pixels
+  const uint64_t odims[3] = {(uint64_t)cout, (uint64_t)Mp, 4};
+  const uint64_t ostr[2] = {(uint64_t)cout * 4, (uint64_t)Mp * cout * 4};
+  const uint32_t obox[3] = {32, (uint32_t)TC_BM, 1};
+  if ((rc = make_tensor_map_f32(&tmOut, t_out, 3, odims, ostr, obox))) return rc;
   UpPhaseArgs a{t_out, (int)Mp, cout, Cin, W + 1};
   const int group = 4 * (cout / TC_BN);  // tiles that share one m-tile: all phases x n-tiles
   const int n_tiles = group * (int)((Mp + TC_BM - 1) / TC_BM);
   int grid = sm_count() / group * group;  // multiple of the group: the phase rotation stays a bijection
   if (grid < group) grid = group;
   if (grid > n_tiles) grid = n_tiles;
-  tc_upconv_phase_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+  tc_upconv_phase_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmOut, a);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
 }
@@ -637,6 +676,11 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
   if ((rc = make_tensor_map_bf16(&tmA_lo, xs_lo, 4, adims, astr, abox))) return rc;
   if ((rc = make_tensor_map_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox))) return rc;
   if ((rc = make_tensor_map_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox))) return rc;
+  CUtensorMap tmOut;  // output [B][H][W][N] fp32, box = 32 channels x the tile's pixel box
+  const uint64_t odims[4] = {(uint64_t)a.N, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+  const uint64_t ostr[3] = {(uint64_t)a.N * 4, (uint64_t)a.W * a.N * 4, (uint64_t)a.H * a.W * a.N * 4};
+  const uint32_t obox[4] = {32, (uint32_t)t.bw, (uint32_t)t.bh, (uint32_t)t.bb};
+  if ((rc = make_tensor_map_f32(&tmOut, a.out, 4, odims, ostr, obox))) return rc;
 
   static thread_local bool attr_set[2] = {false, false};
   const int which = taps == 9 ? 1 : 0;
@@ -648,9 +692,9 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
   const int n_tiles = t.tiles_x * t.tiles_y * t.tiles_b * (a.N / TC_BN);
   dim3 grid(n_tiles < sm_count() ? n_tiles : sm_count());
   if (taps == 9)
-    tc_conv_kernel<9><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a, t);
+    tc_conv_kernel<9><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmOut, a, t);
   else
-    tc_conv_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a, t);
+    tc_conv_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmOut, a, t);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
 }
