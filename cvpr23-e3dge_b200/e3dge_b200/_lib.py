@@ -108,6 +108,8 @@ _PROTOTYPES = {
     "e3_torgb_bwd": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, _fp, c_size_t, _fp]),
     "e3_modconv_styles_bwd": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, _fp, _fp]),
     "e3_torgb_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, _fp, c_int, c_int, c_int, c_int, _fp]),
+    "e3_local_feature_query": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, _fp, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, _fp, _fp, _fp, _fp, _fp]),
     "e3_pack_inversion_record": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int64, _fp, _fp]),
     "e3_ffma_peak_probe": (c_int, [c_int, _fp, _fp]),
     "e3_ffma_peak_probe_sink_floats": (c_size_t, []),
@@ -148,7 +150,9 @@ KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
                     "e3_styled_conv3x3_up_fwd": 3, "e3_styled_conv3x3_up_fwd_split": 3,
                     "e3_styled_conv3x3_fwd_presplit": 1, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
                     "e3_torgb_bwd": 2, "e3_modconv_styles_bwd": 1,
-                    "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1}
+                    "e3_local_feature_query": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, _fp, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, _fp, _fp, _fp, _fp, _fp]),
+    "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1, "e3_local_feature_query": 1}
 launch_count = 0
 
 

@@ -386,6 +386,27 @@ int e3_pack_inversion_record(const float* w_plus, const float* w_dec, int n_late
 int e3_ffma_peak_probe(int iters, float* sink, void* stream);
 size_t e3_ffma_peak_probe_sink_floats(void);
 
+/* ----------------------------------------------------------------------------------
+ * Local branch, first row of SURVEY.md section 8(f): pixel-aligned feature query.
+ * Replaces HGPIFuNetGAN.query(points, calibs, ..., im_feat=F) of the reference
+ * (project/vendor/pifu/lib/model/HGPIFuGANNet.py:85-150; callers e3dge_full_runner.py:219-226,
+ * 244-250, 271-278): perspective projection of every point with the [3x4] rows of its image's
+ * calibration (vendor/pifu/lib/geometry.py:108-135, including the batch-wide "look at -z" sign taken
+ * from point 0 of image 0), y flip, in-image test, and a bilinear zero-padded grid_sample
+ * (align_corners=False; geometry.py:64-80) of a C-channel feature map.
+ *   feat_nhwc [B,H,W,C] channels-last (e3_nchw_to_nhwc of the reference's [B,C,H,W] map), C % 4 == 0;
+ *   points: element (b, k, n) at points[b*pts_batch_stride + k*pts_coord_stride + n*pts_point_stride]
+ *           ([B,3,N] as the reference passes them: strides (3N, N, 1); a renderer `points` output
+ *           [B,N,3]: (3N, 1, 3));   calibs [B][calib_stride] row-major, first 12 floats of each used;
+ *   outputs (each may be NULL): feats [B,N,C] (the layout the caller permutes the reference's [B,C,N]
+ *           into), proj_xy [B,2,N], depth [B,1,N], in_img [B,N] (0 / 1).  feats == NULL = the
+ *           reference's return_projection_only. */
+int e3_local_feature_query(const float* feat_nhwc, const float* points, int64_t pts_batch_stride,
+                           int64_t pts_coord_stride, int64_t pts_point_stride, const float* calibs,
+                           int calib_stride, int batch, int n_points, int h, int w, int c,
+                           float* feats, float* proj_xy, float* depth, unsigned char* in_img,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,3 +180,21 @@ def test_visibility_queries_vs_reference_fixture():
     for k, v in got.items():
         assert tuple(v.shape) == gold[k].shape
         assert rel_linf(v, gold[k]) < 1e-4, k
+
+
+def test_local_feature_query_oracle_vs_reference_fixture():
+    """oracle/local_query_oracle.py against tests/golden/local_query.npz, recorded from the reference's own
+    HGPIFuNetGAN.query / geometry.perspective / geometry.index (oracle/gen_golden_local_query.py): both
+    signs of the camera's z axis, points inside and far outside the frustum."""
+    import os
+    import numpy as np
+    from oracle import local_query_oracle as LQ
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "local_query.npz"))
+    for name in ("neg_z", "pos_z"):
+        t = lambda k: torch.from_numpy(z[f"{name}.{k}"])
+        out = LQ.local_feature_query(t("points"), t("calibs"), t("feat"))
+        assert torch.equal(out["in_img"], t("in_img"))
+        for k in ("proj_xy", "depth", "feats"):
+            ref = t(k)
+            assert (out[k] - ref).abs().max().item() <= 2e-6 * max(ref.abs().max().item(), 1.0), (name, k)
+        assert out["in_img"].float().mean().item() > 0.2 and (~out["in_img"]).float().mean().item() > 0.2
