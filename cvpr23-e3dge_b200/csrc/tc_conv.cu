@@ -16,6 +16,8 @@
 //               128x128x16 per stage), tcgen05.commit releases the stage / signals the epilogue;
 //   warps 2..9  epilogue: tcgen05.ld (two warps per 32-lane quarter, half the columns each), demodulation + noise +
 //               bias + leaky-ReLU*sqrt(2) (StyledConv, stylesdf_model.py:494-507), fp32 NHWC store.
+#include <stdlib.h>
+
 #include "tcgen05.cuh"
 #include "modconv.cuh"
 
@@ -321,6 +323,243 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc::fence_before_thread_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, TC_ACC_BUFS * TC_BN);
+}
+
+// ---- CTA-pair variant of the plain conv (tcgen05 cta_group::2) ---------------------------------
+// One MMA stream per pair of CTAs: M = 256 = the two CTAs' 128-pixel tiles (consecutive m-tiles), N = NT
+// output channels, each CTA holding NT/2 rows of every weight k-block.  Per SM and k-block this halves the
+// weight bytes pulled from L2 and read from shared memory; with NT = 256 a k-block also lasts twice as
+// long (12 x 128 cycles), so the three stages cover the TMA latency that starves the single-CTA kernel
+// (75 % tensor-pipe active with no memory unit above 60 %, profiles/r01k_conv_tc_kernel.txt); with
+// NT = 128 the smaller stage (48 KB) buys a fourth one.  Barrier wiring as in the paired render kernel:
+// both CTAs' TMA loads are counted on the leader's `full`, tcgen05.commit multicasts `empty` / `acc_full`
+// to both, the peer's epilogue warps release the accumulator on the leader's `acc_empty` with a relaxed
+// remote arrive.
+template <int NT>
+struct PairCfg {
+  static constexpr int kBHalfBytes = (NT / 2) * 128;                 // one of hi / lo: NT/2 rows x 64 bf16
+  static constexpr int kStageBytes = 2 * TC_TILE_BYTES + 2 * kBHalfBytes;
+  static constexpr int kStages = NT == 256 ? 3 : 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + TC_OUT_GROUPS * TC_OUT_CHUNK_BYTES + 256 + 1024;
+};
+
+template <int TAPS, int NT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvGemmArgs a,
+                    const __grid_constant__ TcTile t) {
+  using Cfg = PairCfg<NT>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* out_stage = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_GROUPS * TC_OUT_CHUNK_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + TC_ACC_BUFS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_BUFS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles_n = a.N / NT;
+  const int m_tiles = t.tiles_x * t.tiles_y * t.tiles_b;
+  const int n_pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n;
+  const int n_pairs = (int)gridDim.x / 2, pair = (int)blockIdx.x / 2;
+  const int kpt = a.Cin / TC_BK, nkb = TAPS * kpt;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&tmA_hi);
+    tc::prefetch_tensormap(&tmA_lo);
+    tc::prefetch_tensormap(&tmB_hi);
+    tc::prefetch_tensormap(&tmB_lo);
+    tc::prefetch_tensormap(&tmOut);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+#pragma unroll
+    for (int s = 0; s < TC_ACC_BUFS; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 2 * TC_EPI_WARPS);  // the epilogue warps of both CTAs (leader's barrier is used)
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tc::tmem_alloc_pair(tmem_slot, TC_ACC_BUFS * NT);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair tile -> this CTA's pixel box (m-tile 2*pt + rank; past the last one = all out of range: the loads
+  // zero-fill, the stores clip) and first channel
+  auto tile_coords = [&](int tile, int& x0, int& y0, int& b0, int& n0) {
+    const int nt = tile % n_tiles_n, mt = (tile / n_tiles_n) * 2 + (int)rank;
+    const int tx = mt % t.tiles_x, ty = (mt / t.tiles_x) % t.tiles_y, tb = mt / (t.tiles_x * t.tiles_y);
+    x0 = tx * t.bw, y0 = ty * t.bh, b0 = tb * t.bb, n0 = nt * NT;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < n_pair_tiles; tile += n_pairs) {
+        int x0, y0, b0, n0;
+        tile_coords(tile, x0, y0, b0, n0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / kpt, kc = kb - tap * kpt;
+          int dx = (TAPS == 9) ? tap % 3 - 1 : 0, dy = (TAPS == 9) ? tap / 3 - 1 : 0, bc = b0;
+          if (TAPS == 9 && a.planar) {
+            const int ky = tap / 3, kx = tap % 3;
+            dx = kx >> 1, dy = ky >> 1, bc = ((ky & 1) * 2 + (kx & 1)) * a.B + b0;
+          }
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          const uint32_t lfull = tc::map_to_cta(&full[stage], 0);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          tc::tma_load_4d_pair(st, &tmA_hi, lfull, kc * TC_BK, x0 + dx, y0 + dy, bc);
+          tc::tma_load_4d_pair(st + TC_TILE_BYTES, &tmA_lo, lfull, kc * TC_BK, x0 + dx, y0 + dy, bc);
+          const int brow = n0 + (int)rank * (NT / 2);
+          tc::tma_load_2d_pair(st + 2 * TC_TILE_BYTES, &tmB_hi, lfull, tap * a.Cin + kc * TC_BK, brow);
+          tc::tma_load_2d_pair(st + 2 * TC_TILE_BYTES + Cfg::kBHalfBytes, &tmB_lo, lfull, tap * a.Cin + kc * TC_BK, brow);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = tc::make_idesc_bf16_f32(256, NT);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = pair; tile < n_pair_tiles; tile += n_pairs, ++it) {
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc::fence_after_thread_sync();
+        const uint32_t dcol = tmem_base + buf * NT;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc::fence_after_thread_sync();
+          const uint32_t sb = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t dA_hi = tc::make_smem_desc_sw128(sb);
+          const uint64_t dA_lo = tc::make_smem_desc_sw128(sb + TC_TILE_BYTES);
+          const uint64_t dB_hi = tc::make_smem_desc_sw128(sb + 2 * TC_TILE_BYTES);
+          const uint64_t dB_lo = tc::make_smem_desc_sw128(sb + 2 * TC_TILE_BYTES + Cfg::kBHalfBytes);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 16; ++ks) {
+            const uint64_t ah = tc::advance_desc_k(dA_hi, ks), al = tc::advance_desc_k(dA_lo, ks);
+            const uint64_t bh = tc::advance_desc_k(dB_hi, ks), bl = tc::advance_desc_k(dB_lo, ks);
+            tc::mma_bf16_ss_pair(dcol, ah, bh, idesc, (kb | ks) != 0);
+            tc::mma_bf16_ss_pair(dcol, ah, bl, idesc, true);
+            tc::mma_bf16_ss_pair(dcol, al, bh, idesc, true);
+          }
+          tc::mma_commit_pair(&empty[stage], 3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::mma_commit_pair(&acc_full[buf], 3);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int ix = m % t.bw, iy = (m / t.bw) % t.bh, ib = m / (t.bw * t.bh);
+    const float nw = (a.mode == 1) ? a.noise_w[0] : 0.f;
+    uint8_t* obuf = out_stage + chalf * TC_OUT_CHUNK_BYTES;
+    uint32_t it = 0;
+    for (int tile = pair; tile < n_pair_tiles; tile += n_pairs, ++it) {
+      int x0, y0, b0, n0;
+      tile_coords(tile, x0, y0, b0, n0);
+      const uint32_t buf = it & 1, use = it >> 1;
+      const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
+      const bool valid = b < a.B;
+      const int p = y * a.W + x;
+      const float nz = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
+      mbar_wait(&acc_full[buf], use & 1);
+      tc::fence_after_thread_sync();
+      constexpr int kChunksPerWarp = NT / 32 / (TC_EPI_WARPS / 4);
+#pragma unroll 1
+      for (int chunk = chalf * kChunksPerWarp; chunk < (chalf + 1) * kChunksPerWarp; ++chunk) {
+        float v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT + chunk * 32, v);
+        if (chunk == (chalf + 1) * kChunksPerWarp - 1) {  // this warp's share is read: tell the leader's MMA thread
+          tc::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&acc_empty[buf]);
+            else tc::mbar_arrive_cluster_relaxed(tc::map_to_cta(&acc_empty[buf], 0));
+          }
+        }
+        const int nb = n0 + chunk * 32;
+        if (valid && a.mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float tt = fmaf(v[j], a.d[(size_t)b * a.N + nb + j], nz) + a.act_bias[nb + j];
+            v[j] = (tt > 0.f ? tt : 0.2f * tt) * 1.41421356237309515f;
+          }
+        } else if (valid && a.mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= a.d[(size_t)b * a.N + nb + j];
+        }
+        tc::named_bar_sync(2 + chalf, 128);
+        tc::stage_row32(obuf, m, v);
+        fence_proxy_async();
+        tc::named_bar_sync(2 + chalf, 128);
+        if (q == 0 && lane == 0) {
+          tc::tma_store_4d(&tmOut, obuf, nb, x0, y0, b0);
+          tc::tma_store_commit_and_wait_read();
+        }
+      }
+    }
+    if (q == 0 && lane == 0) tc::tma_store_wait_all();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  cluster_sync_all();  // the peer's TMEM / barriers stay valid until both CTAs are done
+  if (warp == 1) tc::tmem_dealloc_pair(tmem_base, TC_ACC_BUFS * NT);
+}
+
+template <int TAPS, int NT>
+static int launch_conv_pair(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                            const CUtensorMap& tmB_lo, const CUtensorMap& tmOut, const ConvGemmArgs& a,
+                            const TcTile& t, cudaStream_t stream) {
+  auto* fn = tc_conv_pair_kernel<TAPS, NT>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NT>::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = t.tiles_x * t.tiles_y * t.tiles_b;
+  const int n_pair_tiles = ((m_tiles + 1) / 2) * (a.N / NT);
+  int pairs = sm_count() / 2;
+  if (pairs > n_pair_tiles) pairs = n_pair_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = PairCfg<NT>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  E3_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmOut, a, t));
+  return E3_OK;
+}
+
+// E3DGE_CONV_PAIR=0 selects the single-CTA kernel (measurement aid)
+static bool conv_pairs_enabled() {
+  const char* e = getenv("E3DGE_CONV_PAIR");
+  return !(e && e[0] == '0');
 }
 
 // ---- upsampling conv on the tensor cores: parity-phase formulation ------------------------------
@@ -682,6 +921,16 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
   const uint32_t obox[4] = {32, (uint32_t)t.bw, (uint32_t)t.bh, (uint32_t)t.bb};
   if ((rc = make_tensor_map_f32(&tmOut, a.out, 4, odims, ostr, obox))) return rc;
 
+  if (taps == 9 && conv_pairs_enabled()) {
+    // CTA pairs: the weight maps' box is one CTA's half of the N tile
+    const int NT = (a.N % 256 == 0) ? 256 : 128;
+    const uint32_t pbox[2] = {(uint32_t)TC_BK, (uint32_t)(NT / 2)};
+    CUtensorMap pB_hi, pB_lo;
+    if ((rc = make_tensor_map_bf16(&pB_hi, w_hi, 2, bdims, bstr, pbox))) return rc;
+    if ((rc = make_tensor_map_bf16(&pB_lo, w_lo, 2, bdims, bstr, pbox))) return rc;
+    return NT == 256 ? launch_conv_pair<9, 256>(tmA_hi, tmA_lo, pB_hi, pB_lo, tmOut, a, t, stream)
+                     : launch_conv_pair<9, 128>(tmA_hi, tmA_lo, pB_hi, pB_lo, tmOut, a, t, stream);
+  }
   static thread_local bool attr_set[2] = {false, false};
   const int which = taps == 9 ? 1 : 0;
   if (!attr_set[which]) {
