@@ -330,8 +330,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // output channels, each CTA holding NT/2 rows of every weight k-block.  Per SM and k-block this halves the
 // weight bytes pulled from L2 and read from shared memory; with NT = 256 a k-block also lasts twice as
 // long (12 x 128 cycles), so the three stages cover the TMA latency that starves the single-CTA kernel
-// (75 % tensor-pipe active with no memory unit above 60 %, profiles/r01k_conv_tc_kernel.txt); with
-// NT = 128 the smaller stage (48 KB) buys a fourth one.  Barrier wiring as in the paired render kernel:
+// (75 % tensor-pipe active with no memory unit above 60 %, profiles/r01k_conv_tc_kernel.txt).  (NT = 128
+// with four 48 KB stages was measured too: no faster than the single-CTA kernel, not instantiated.)  Barrier wiring as in the paired render kernel:
 // both CTAs' TMA loads are counted on the leader's `full`, tcgen05.commit multicasts `empty` / `acc_full`
 // to both, the peer's epilogue warps release the accumulator on the leader's `acc_empty` with a relaxed
 // remote arrive.
@@ -921,15 +921,20 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
   const uint32_t obox[4] = {32, (uint32_t)t.bw, (uint32_t)t.bh, (uint32_t)t.bb};
   if ((rc = make_tensor_map_f32(&tmOut, a.out, 4, odims, ostr, obox))) return rc;
 
-  if (taps == 9 && conv_pairs_enabled()) {
-    // CTA pairs: the weight maps' box is one CTA's half of the N tile
-    const int NT = (a.N % 256 == 0) ? 256 : 128;
-    const uint32_t pbox[2] = {(uint32_t)TC_BK, (uint32_t)(NT / 2)};
-    CUtensorMap pB_hi, pB_lo;
-    if ((rc = make_tensor_map_bf16(&pB_hi, w_hi, 2, bdims, bstr, pbox))) return rc;
-    if ((rc = make_tensor_map_bf16(&pB_lo, w_lo, 2, bdims, bstr, pbox))) return rc;
-    return NT == 256 ? launch_conv_pair<9, 256>(tmA_hi, tmA_lo, pB_hi, pB_lo, tmOut, a, t, stream)
-                     : launch_conv_pair<9, 128>(tmA_hi, tmA_lo, pB_hi, pB_lo, tmOut, a, t, stream);
+  // CTA pairs pay when N allows 256-column tiles (measured: 128-column pair tiles are no faster than the
+  // single-CTA kernel) and the 256 x 256 tiles fill whole waves of the 74 pairs (conv1 of the 256^2 decoder
+  // has 256 of them = 3.5 waves and loses to 1024 single-CTA tiles on 148 SMs)
+  if (taps == 9 && a.N % 256 == 0 && conv_pairs_enabled()) {
+    const int m_tiles = t.tiles_x * t.tiles_y * t.tiles_b;
+    const int n_pair_tiles = ((m_tiles + 1) / 2) * (a.N / 256), pairs = sm_count() / 2;
+    const int waves = (n_pair_tiles + pairs - 1) / pairs;
+    if (n_pair_tiles * 10 >= waves * pairs * 9) {
+      const uint32_t pbox[2] = {(uint32_t)TC_BK, 128};  // the weight maps' box is one CTA's half of the N tile
+      CUtensorMap pB_hi, pB_lo;
+      if ((rc = make_tensor_map_bf16(&pB_hi, w_hi, 2, bdims, bstr, pbox))) return rc;
+      if ((rc = make_tensor_map_bf16(&pB_lo, w_lo, 2, bdims, bstr, pbox))) return rc;
+      return launch_conv_pair<9, 256>(tmA_hi, tmA_lo, pB_hi, pB_lo, tmOut, a, t, stream);
+    }
   }
   static thread_local bool attr_set[2] = {false, false};
   const int which = taps == 9 ? 1 : 0;
