@@ -330,7 +330,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // output channels, each CTA holding NT/2 rows of every weight k-block.  Per SM and k-block this halves the
 // weight bytes pulled from L2 and read from shared memory; with NT = 256 a k-block also lasts twice as
 // long (12 x 128 cycles), so the three stages cover the TMA latency that starves the single-CTA kernel
-// (75 % tensor-pipe active with no memory unit above 60 %, profiles/r01k_conv_tc_kernel.txt).  (NT = 128
+// (75 % tensor-pipe active with no memory unit above 60 %, profiles/r01l_conv_tc_kernel.txt).  (NT = 128
 // with four 48 KB stages was measured too: no faster than the single-CTA kernel, not instantiated.)  Barrier wiring as in the paired render kernel:
 // both CTAs' TMA loads are counted on the leader's `full`, tcgen05.commit multicasts `empty` / `acc_full`
 // to both, the peer's epilogue warps release the accumulator on the leader's `acc_empty` with a relaxed
