@@ -325,6 +325,31 @@ def test_fused_conv_pair_and_side_stream_prepare_are_bit_identical_to_the_layerw
     assert rel_linf(img.detach().cpu(), full_fused.cpu()) < 1e-5
 
 
+def test_cta_pair_conv_is_bit_identical_to_the_single_cta_kernel(monkeypatch):
+    """256-channel plain convs whose tiles fill whole waves run on CTA pairs (tcgen05 cta_group::2, 256 x 256
+    tiles); the products and their accumulation order per output are those of the single-CTA kernel."""
+    from e3dge_b200.stylesdf_model import StyledConv
+    g = np.random.Generator(np.random.PCG64(2024))
+    f32 = lambda *s: torch.from_numpy(g.standard_normal(s).astype(np.float32))
+    cin = cout = 256
+    m = StyledConv(cin, cout, 3, 512)
+    m.load_state_dict({"conv.weight": f32(1, cout, cin, 3, 3), "conv.modulation.weight": f32(cin, 512),
+                       "conv.modulation.bias": 1 + 0.1 * f32(cin), "noise.weight": 0.1 * f32(1),
+                       "activate.bias": 0.1 * f32(cout), "bias": torch.zeros(1, cout, 1, 1)}, strict=False)
+    m = m.cuda()
+    _set_backend(m, "tensor_cores")
+    # 512 pair tiles = 6.9 waves of 74 pairs; 147 m-tiles of two 8x8 images (the last one half empty) = 74
+    # pair tiles, the last pair's second CTA working on a tile past the end
+    for batch, hw in ((8, 128), (293, 8)):
+        x, lat, noise = f32(batch, cin, hw, hw).cuda(), f32(batch, 512).cuda(), f32(1, 1, hw, hw).cuda()
+        with torch.no_grad():
+            monkeypatch.setenv("E3DGE_CONV_PAIR", "0")
+            y_single = m(x, lat, noise=noise)
+            monkeypatch.setenv("E3DGE_CONV_PAIR", "1")
+            y_pair = m(x, lat, noise=noise)
+        assert torch.equal(y_single, y_pair), (batch, hw)
+
+
 def test_tensor_core_request_on_unsupported_shape_fails_loudly():
     from e3dge_b200.stylesdf_model import StyledConv
     m = StyledConv(16, 24, 3, 512).cuda()
