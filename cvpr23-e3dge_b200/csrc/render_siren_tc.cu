@@ -5,32 +5,37 @@
 // the eight 256x256 hidden-layer contractions run on the 5th-gen tensor cores instead of the
 // FFMA pipe:
 //
-//   * a tile = 128 sample rows (UMMA M = 128) = floor(128/S) whole rays;
+//   * a tile = 128 sample rows (UMMA M = 128 per CTA) = floor(128/S) whole rays;
 //   * the hidden state lives in shared memory as the UMMA A operand: bf16 hi + bf16 lo
 //     (h = hi + lo to 2^-17), K-major SWIZZLE_128B, 4 k-blocks x 16 KB each — written in place
 //     by the epilogue of the previous layer;
-//   * per layer D[128x256] (fp32 in TMEM) = h_hi*W_hi^T + h_lo*W_hi^T + h_hi*W_lo^T:
-//     48 tcgen05.mma 128x256x16 issued by one thread; the three-product split keeps the result
-//     fp32-faithful (measured 5e-5..1.5e-4 end to end vs 2..5e-2 for plain bf16 operands; the
-//     parity bar is 1e-3);
-//   * weights: 2 MB of pre-split, pre-swizzled bf16 tiles streamed from L2 by cp.async.bulk
-//     (TMA) through a 4 x 16 KB full/empty mbarrier ring, one 128(n) x 64(k) tile per stage;
-//   * 16 epilogue warps: tcgen05.ld -> FiLM (bias folded into beta', table in shared memory) ->
-//     accurate sin -> hi/lo split -> swizzled st.shared of the next layer's A operand; layer 0
-//     (K = 3), the sdf / rgb heads, the view-direction rank-3 update, the transmittance scan and
-//     the weighted feature sum stay on the CUDA cores.
+//   * per layer D[128x256] (fp32 in TMEM) = h_hi*W_hi^T + h_lo*W_hi^T + h_hi*W_lo^T: the three-product
+//     split keeps the result fp32-faithful (measured 5e-5..1.5e-4 end to end vs 2..5e-2 for plain bf16
+//     operands; the parity bar is 1e-3);
+//   * default (EPI = 7): the two CTAs of a cluster form a PAIR and run their tiles in lockstep through one
+//     tcgen05.mma.cta_group::2 stream issued by the leader — 48 MMAs 256x256x16 per layer, M = 128 rows
+//     from each CTA, every CTA's ring holding one N-half of each 256 x 64 weight block (2 MB of pre-split,
+//     pre-swizzled bf16 tiles streamed from L2 by tensor-map TMA through a 4 x 16 KB full/empty mbarrier
+//     ring, both CTAs' bytes counted on the leader's barrier).  One CTA per MMA stream (EPI = 3 / 0, 128x256x16
+//     MMAs over paired ring stages) is kept for A/B timing: there the MMAs are paced by the shared-memory
+//     pipe (A 4 KB + B 8 KB per MMA + weight TMA writes + epilogue stores);
+//   * 16 epilogue warps per CTA: tcgen05.ld -> FiLM (bias folded into beta', table in shared memory) ->
+//     2-term 2pi reduction + MUFU sin -> hi/lo split -> swizzled st.shared of the next layer's A operand,
+//     the arithmetic packed two channels per instruction (FFMA2 / FADD2); layer 0 (K = 3), the sdf / rgb
+//     heads, the view-direction rank-3 update, the transmittance scan and the weighted feature sum stay
+//     on the CUDA cores.
 //
 // Layer pipelining.  Layer l+1 contracts over ALL outputs of layer l, but k-block j of that
 // contraction only needs output channels [64j, 64j+64).  The epilogue therefore walks a layer in
-// four 64-channel blocks and publishes each one (a_ready[j]); the MMA warp starts layer l+1's
-// k-block j as soon as it lands, accumulating into the OTHER half of TMEM (512 columns = two
-// 128x256 fp32 accumulators, ping-pong by layer parity).  Three quarters of a layer's MMA time
-// hide under the epilogue of the previous layer; overwriting the A operand in place is safe
-// because layer l's MMAs have all completed (d_ready) before its epilogue starts.
+// four 64-channel blocks and publishes each one (a_ready[j]; the first and last block in two halves,
+// a_half / a_tail); the MMA thread starts layer l+1's k-block j as soon as it lands, accumulating into the
+// OTHER half of TMEM (512 columns = two 128x256 fp32 accumulators, ping-pong by layer parity).  Overwriting
+// the A operand in place is safe because layer l's MMAs have all completed (d_ready) before its epilogue
+// starts.  In a pair every publish goes to the leader's barrier (the peer's warps arrive remotely, relaxed).
 //
-// Warp roles: warp 0 = TMA weight producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 =
-// compute (TMEM lane quarter = warp % 4; the four warps of a quarter take 16 columns each of a
-// 64-channel block — 4 warps per scheduler hide the sin / LDS / tcgen05.ld latencies).  The sdf->alpha->scan work of a tile overlaps with the view-layer MMAs.
+// Warp roles: warp 0 = TMA weight producer, warp 1 = TMEM owner (+ MMA issuer in the leader), warps 2..17 =
+// compute (TMEM lane quarter = warp % 4; the four warps of a quarter share the columns of a block).  The
+// sdf->alpha->scan work of a tile overlaps with the view-layer MMAs.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
