@@ -131,6 +131,16 @@ def run_ours(args):
     G, sd = build_generator(dev)
     host = {k: v.pin_memory() for k, v in make_inputs(rank).items()}
     resident = {k: v.to(dev) for k, v in host.items()}
+    # e2e: the step's inputs (latents, cameras: 172 KB) travel as ONE pinned buffer and one copy per step
+    # instead of six small ones; the device side slices views out of it
+    offs, total = {}, 0
+    for k, v in host.items():
+        offs[k] = (total, v.numel(), tuple(v.shape))
+        total += (v.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+    host_packed = torch.empty(total).pin_memory()
+    for k, v in host.items():
+        o, n, _ = offs[k]
+        host_packed[o:o + n].copy_(v.reshape(-1))
     n_lat = resident["w_dec"].shape[1]
     target = torch.zeros(BATCH, 3, SIZE, SIZE, device=dev)
     rec_local = torch.empty(BATCH, par.record_length(n_lat), device=dev)
@@ -149,7 +159,8 @@ def run_ours(args):
         return out
 
     def step_e2e():
-        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        packed = host_packed.to(dev, non_blocking=True)
+        inp = {k: packed[o:o + n].view(shape) for k, (o, n, shape) in offs.items()}
         out = step(inp)
         img_host.copy_(out["gen_imgs"], non_blocking=True)
         return out
@@ -197,7 +208,7 @@ def run_ours(args):
                        "l2": "256 MiB memset between timed steps, outside the per-step CUDA-event pairs",
                        "randomize_noise": True},
             "e2e": {"value": e2e_value, "unit": "frames/s",
-                    "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()),
+                    "h2d_bytes_per_step": host_packed.numel() * 4,
                     "d2h_bytes_per_step": img_host.numel() * 4},
             "gpu_launches": launches, "clocks": clocks}
 
