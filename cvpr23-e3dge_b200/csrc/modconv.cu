@@ -405,18 +405,31 @@ __global__ void __launch_bounds__(256) upconv_blur_act_kernel(const __grid_const
             a.t + ((size_t)(pr * 2 + pc) * Mp + ((size_t)b * Hp + i) * Wp + (ok ? j : 0)) * a.cout + o);
         tv[c] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      // separable: the row's four horizontal blur outputs first (4 taps each), then into the <= 4 output
+      // rows this T row feeds: 64 + 16..64 FMAs per row instead of up to 256
+      float4 hr[4];
 #pragma unroll
-      for (int c = 0; c < 7; ++c) {
+      for (int kx = 0; kx < 4; ++kx) {
+        hr[kx] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int ky = 0; ky < 4; ++ky)
+        for (int c = 0; c < 7; ++c) {
+          const float k = blur_w(c, kx);
+          if (k != 0.f) {
+            hr[kx].x = fmaf(k, tv[c].x, hr[kx].x), hr[kx].y = fmaf(k, tv[c].y, hr[kx].y);
+            hr[kx].z = fmaf(k, tv[c].z, hr[kx].z), hr[kx].w = fmaf(k, tv[c].w, hr[kx].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const float k = blur_w(r, ky);
+        if (k != 0.f) {
 #pragma unroll
           for (int kx = 0; kx < 4; ++kx) {
-            const float k = blur_w(r, ky) * blur_w(c, kx);
-            if (k != 0.f) {
-              acc[ky][kx].x = fmaf(k, tv[c].x, acc[ky][kx].x), acc[ky][kx].y = fmaf(k, tv[c].y, acc[ky][kx].y);
-              acc[ky][kx].z = fmaf(k, tv[c].z, acc[ky][kx].z), acc[ky][kx].w = fmaf(k, tv[c].w, acc[ky][kx].w);
-            }
+            acc[ky][kx].x = fmaf(k, hr[kx].x, acc[ky][kx].x), acc[ky][kx].y = fmaf(k, hr[kx].y, acc[ky][kx].y);
+            acc[ky][kx].z = fmaf(k, hr[kx].z, acc[ky][kx].z), acc[ky][kx].w = fmaf(k, hr[kx].w, acc[ky][kx].w);
           }
+        }
       }
     }
     const float4 dv = *reinterpret_cast<const float4*>(a.d + (size_t)b * a.cout + o);

@@ -552,6 +552,16 @@ static int launch_conv_pair(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent kernel: no more pairs than can be co-resident as clusters
+  static thread_local int max_clusters = 0;
+  if (!max_clusters) {
+    cfg.gridDim = dim3(2 * (sm_count() / 2));
+    int n = 0;
+    E3_CUDA(cudaOccupancyMaxActiveClusters(&n, fn, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  if (pairs > max_clusters) pairs = max_clusters;
+  cfg.gridDim = dim3(2 * pairs);
   E3_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmOut, a, t));
   return E3_OK;
 }
