@@ -267,6 +267,7 @@ def _set_backend(module, backend):
     (128, 128, 8, 3, False), (128, 128, 8, 3, True),      # 8x8 maps: two images per tile, odd batch
     (256, 512, 64, 1, False), (512, 256, 64, 1, True),    # conv1 / first up-conv of the 256^2 decoder
     (128, 128, 256, 1, False),                            # last conv: 128-wide row tiles
+    (64, 128, 12, 2, True), (64, 256, 5, 3, True),        # up-conv on maps that are not powers of two (odd too)
 ])
 def test_tensor_core_conv_vs_fp32_path_and_oracle(cin, cout, hw, batch, up):
     from e3dge_b200.stylesdf_model import StyledConv
