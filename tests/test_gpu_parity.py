@@ -602,3 +602,26 @@ def test_generator_forward_is_cuda_graph_capturable():
         torch.cuda.synchronize()
         got = out.clone()
         assert torch.equal(got, step())
+
+
+def test_graphed_call_replays_the_generator_pass_on_new_inputs():
+    """e3dge_b200.graphed.GraphedCall: one CUDA-graph launch per generator pass; new latents / cameras written
+    into the static buffers (here through one packed buffer, as bench.py's e2e step does) take effect."""
+    from e3dge_b200.graphed import GraphedCall
+    G, sd = _build(64, 16, 41, "sharp")
+    a = _cuda(P.make_inputs(41, 2, decoder_layout(64, 16), 16))
+    b = _cuda(P.make_inputs(42, 2, decoder_layout(64, 16), 16))
+    static = {k: v.clone() for k, v in a.items()}
+
+    def fwd(inp):
+        with torch.no_grad():
+            return G([inp["w"], inp["w_dec"]], inp["cam_poses"], inp["focal"], inp["near"], inp["far"],
+                     input_is_latent=True, randomize_noise=False)
+    call = GraphedCall(lambda: fwd(static))
+    assert call.launches > 10
+    for inp in (b, a):
+        for k in static:
+            static[k].copy_(inp[k])
+        out = call()
+        ref = fwd(inp)
+        assert torch.equal(out["gen_imgs"], ref["gen_imgs"]) and torch.equal(out["features"], ref["features"])
