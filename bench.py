@@ -180,6 +180,8 @@ def run_ours(args):
             par.pack_records(static["w"], static["w_dec"], out["gen_imgs"], target, out=rec_local)
         return out
     try:
+        if os.environ.get("E3DGE_BENCH_EAGER"):  # profiling aid: every kernel launched from Python, in order
+            raise RuntimeError("E3DGE_BENCH_EAGER")
         gcall = GraphedCall(core)
         launch_mode = ("CUDA-graph replay of G_pred_latents.forward + record kernel "
                        "(e3dge_b200.graphed.GraphedCall); `eager` = the same step launched from Python")
