@@ -194,7 +194,8 @@ def run_ours(args):
             def __call__(self):
                 return core()
         gcall = _Eager()
-        launch_mode = f"eager launches from Python (graph capture failed: {type(exc).__name__})"
+        why = "E3DGE_BENCH_EAGER set" if str(exc) == "E3DGE_BENCH_EAGER" else f"graph capture failed: {type(exc).__name__}"
+        launch_mode = f"eager launches from Python ({why})"
 
     def step_graph():
         out = gcall()
