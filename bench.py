@@ -236,7 +236,7 @@ def run_ours(args):
 
     with ClockSampler(local) as clk:
         time.sleep(1.0)  # nvidia-smi's start-up holds driver locks: keep it out of the timed region
-        for _ in range(40):  # ~0.2 s of untimed passes: GPU and host leave their idle states before the W warm-ups
+        for _ in range(5):  # a few untimed passes: GPU and host leave their idle states before the W warm-ups
             step_graph()
         sync_all()
         clk.mark()
