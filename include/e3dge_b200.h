@@ -36,6 +36,9 @@ extern "C" {
 #define E3_SIREN_DEPTH 8   /* rendering.depth */
 #define E3_STYLE_DIM 256   /* model.style_dim */
 
+/* 3 = adds e3_styled_conv_pair_fusable / e3_styled_conv3x3_up_fwd_split / e3_styled_conv3x3_fwd_presplit and
+ * e3_local_feature_query; the bf16 part of the up-conv weight image (e3_conv_pack_weight layout 1) is ordered
+ * by output parity phase.  Images packed by an ABI-2 library must be re-packed. */
 int e3_abi_version(void);
 const char* e3_last_error(void);
 
