@@ -52,3 +52,29 @@ def test_oracle_and_contract_against_live_reference():
     assert res["keys_256"] and res["keys_1024"]
     for k, e in res["err"].items():
         assert e < 2e-5, (k, e)
+
+
+def test_local_feature_query_oracle_matches_the_live_reference():
+    """oracle/local_query_oracle.py against the reference's HGPIFuNetGAN.query executed here (fresh random
+    cases, not the committed fixture): SURVEY.md 8f row 1."""
+    script = r"""
+import json, sys, torch
+sys.path.insert(0, %(root)r)
+from oracle import gen_golden_local_query as gen, local_query_oracle as LQ
+res = {}
+for i, args in enumerate(((101, 2, 8, 10, 14, 300, True), (102, 1, 12, 16, 9, 200, False))):
+    feat, pts, calibs = gen.make_case(*args)
+    ref = gen.run(feat, pts, calibs)
+    got = LQ.local_feature_query(pts, calibs, feat)
+    res[str(i)] = {k: float((got[k] - ref[k]).abs().max() / max(float(ref[k].abs().max()), 1.0))
+                   for k in ("proj_xy", "depth", "feats")}
+    res[str(i)]["in_img"] = bool((got["in_img"] == ref["in_img"]).all())
+print("RESULT" + json.dumps(res))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.split("RESULT")[-1])
+    for case in res.values():
+        assert case["in_img"]
+        for k in ("proj_xy", "depth", "feats"):
+            assert case[k] < 2e-6, (k, case[k])
