@@ -33,6 +33,10 @@ for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 import torch  # noqa: E402
 
 SIZE, RES, N_SAMPLES, BATCH, SEED = 256, 64, 24, 8, 2024
+# arithmetic of the timed path, not a precision claim: fp32 tensors in and out; every 256x256 / conv
+# contraction as three bf16 tensor-core products of hi/lo operand halves (hi*hi + lo*hi + hi*lo, ~16-17
+# mantissa bits) accumulated in fp32; layer 0, FiLM, sin, heads, composite, blur in fp32 on the CUDA cores
+DTYPE = "f32 I/O; split-bf16x3 tcgen05 contractions, f32 accumulate"
 METRIC = "inversion frames/sec @256^2 StyleSDF (generator pass: 64x64 rays x 24 samples + decoder)"
 WORKLOAD = ("FFHQ StyleSDF 256^2 inversion, 64 rays x 24 samples, batch=8 per GPU "
             "(BASELINE.json configs[1])")
@@ -113,6 +117,16 @@ def build_generator(device):
                        rendering_options(N_samples=N_SAMPLES), full_pipeline=True).eval()
     G.load_state_dict(sd, strict=True)
     return G.to(device), sd
+
+
+def set_backends(G, which):
+    """"auto" = the tcgen05 split-bf16 kernels wherever the shape allows (default); "fp32" = the exact-fp32
+    CUDA-core kernels for renderer and decoder."""
+    from e3dge_b200.stylesdf_model import ModulatedConv2d
+    G.renderer.backend = "fp32" if which == "fp32" else "tensor_cores"
+    for m in G.modules():
+        if isinstance(m, ModulatedConv2d):
+            m.backend = which
 
 
 def make_inputs(rank):
@@ -243,6 +257,37 @@ def run_ours(args):
         ms_total, _ = timed(step_graph, args.steps, args.warmup)
         ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup))
         ms_eager, launches_eager = timed(lambda: step(resident), args.steps, args.warmup)
+        # the same step on the exact-fp32 back ends (FFMA renderer, FFMA implicit-GEMM convs): every
+        # contraction in plain fp32 like the reference, whole step and end to end
+        exact = None
+        if not args.no_exact_fp32:
+            set_backends(G, "fp32")
+            try:
+                gcall32 = GraphedCall(core)
+
+                def step32():
+                    out = gcall32()
+                    if world > 1:
+                        par.gather_records(rec_local, out=rec_all, equal_shards=True)
+                    return out
+
+                def step32_e2e():
+                    packed_dev.copy_(host_packed, non_blocking=True)
+                    out = step32()
+                    img_host.copy_(out["gen_imgs"], non_blocking=True)
+                    return out
+                n32 = max(3, min(args.steps, 10))
+                ms32, _ = timed(step32, n32, 3)
+                ms32_e2e, _ = timed(step32_e2e, n32, 1)
+                f32 = n32 * BATCH * world
+                exact = {"what": "same step, renderer E3_RENDER_FP32_CUDA_CORES + decoder E3_CONV_FP32_CUDA_CORES "
+                                 "(plain fp32 FFMA contractions), CUDA-graph replay",
+                         "dtype": "f32", "steps": n32, "ms_per_step": ms32 / n32, "value": f32 / (ms32 / 1e3),
+                         "e2e": f32 / (ms32_e2e / 1e3), "unit": "frames/s"}
+            except Exception as exc:  # never lose the headline line to the secondary arm
+                exact = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+            finally:
+                set_backends(G, "auto")
     clocks = clk.summary()
     launches = args.steps * gcall.launches if gcall.launches else launches_eager
     frames = args.steps * BATCH * world
@@ -251,7 +296,7 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic (random latents/cameras, random-init weights)",
             "config": {"workload": WORKLOAD, "size": SIZE, "render_res": RES,
                        "n_samples": N_SAMPLES, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
@@ -264,7 +309,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": img_host.numel() * 4},
             "gpu_launches": launches, "clocks": clocks,
             "eager": {"ms_per_step": ms_eager / args.steps, "value": frames / (ms_eager / 1e3),
-                      "gpu_launches": launches_eager}}
+                      "gpu_launches": launches_eager},
+            "exact_fp32": exact}
 
     if rank == 0:
         line.update(kernel_roofline(G, resident, dev, flush, args))
@@ -458,7 +504,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (random latents/cameras, random-init weights)",
+        "vs_baseline": None, "dtype": "f32 (torch CPU)", "data": "synthetic (random latents/cameras, random-init weights)",
         "config": {"workload": WORKLOAD, "size": SIZE, "render_res": RES, "n_samples": N_SAMPLES,
                    "batch_per_gpu": BATCH},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -474,6 +520,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact-fp32", action="store_true", help="skip the exact-fp32 back-end timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

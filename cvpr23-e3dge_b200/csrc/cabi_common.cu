@@ -33,6 +33,12 @@ int sm_count() {
   return cached;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= E3_MAX_DEVICES) return 0;
+  return dev;
+}
+
 }  // namespace e3
 
 namespace e3 {

@@ -30,6 +30,9 @@ int check_cuda(cudaError_t e, const char* what);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();
+// slot of the calling thread's current device in per-device caches (function attributes, occupancy)
+constexpr int E3_MAX_DEVICES = 64;
+int device_slot();
 
 // ---- device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -548,15 +548,19 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __grid_constant__ ToRg
 }
 
 // ---- image-parallel inversion record ----------------------------------------
-// blockIdx.x = image, blockIdx.y = slice of the image: every slice copies its share of the latents
-// and adds its partial squared / absolute error sums to the record's two metric slots (pre-zeroed).
-__global__ void __launch_bounds__(256) pack_record_kernel(const float* __restrict__ w_plus,
+// One thread-block cluster of RECORD_PARTS CTAs per image (blockIdx.y = image, blockIdx.x = slice): every
+// slice copies its share of the latents and reduces its share of the squared / absolute error; the slices'
+// partial sums meet in CTA 0 of the cluster through distributed shared memory and are added in slice
+// order — no atomics, the record is bit-reproducible.
+constexpr int RECORD_PARTS = 8;
+constexpr int RECORD_THREADS = 512;
+__global__ void __launch_bounds__(RECORD_THREADS) pack_record_kernel(const float* __restrict__ w_plus,
                                                           const float* __restrict__ w_dec,
                                                           int n_latent, const float* __restrict__ image,
                                                           const float* __restrict__ target,
                                                           int64_t image_numel,
                                                           float* __restrict__ record) {
-  const int b = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+  const int b = blockIdx.y, part = blockIdx.x, parts = gridDim.x;
   const int rec_len = 2304 + n_latent * 512 + 2;
   float* rec = record + (size_t)b * rec_len;
   const int tid = part * blockDim.x + threadIdx.x, nthr = parts * blockDim.x;
@@ -572,17 +576,35 @@ __global__ void __launch_bounds__(256) pack_record_kernel(const float* __restric
       ae += fabsf(dlt);
     }
   }
-  __shared__ float red[2][8];
+  __shared__ float red[2][RECORD_THREADS / 32];
+  __shared__ float part_sum[2];
   se = warp_sum(se), ae = warp_sum(ae);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) red[0][warp] = se, red[1][warp] = ae;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s2 = 0.f, a2 = 0.f;
-    for (int i = 0; i < 8; ++i) s2 += red[0][i], a2 += red[1][i];
-    atomicAdd(&rec[rec_len - 2], s2 / (float)image_numel);
-    atomicAdd(&rec[rec_len - 1], a2 / (float)image_numel);
+    for (int i = 0; i < RECORD_THREADS / 32; ++i) s2 += red[0][i], a2 += red[1][i];
+    part_sum[0] = s2, part_sum[1] = a2;
   }
+  if (parts == 1) {  // launched without a cluster (no image): the metric slots are zero
+    if (threadIdx.x == 0) rec[rec_len - 2] = 0.f, rec[rec_len - 1] = 0.f;
+    return;
+  }
+  cluster_sync_all();  // every slice's partial sums are in its shared memory
+  if (part == 0 && threadIdx.x == 0) {
+    float s2 = 0.f, a2 = 0.f;
+    for (int r = 0; r < parts; ++r) {
+      const uint32_t addr = tc::map_to_cta(part_sum, (uint32_t)r);
+      float ps, pa;
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(ps) : "r"(addr));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pa) : "r"(addr + 4));
+      s2 += ps, a2 += pa;
+    }
+    rec[rec_len - 2] = s2 / (float)image_numel;
+    rec[rec_len - 1] = a2 / (float)image_numel;
+  }
+  cluster_sync_all();  // no slice exits while CTA 0 may still read its shared memory
 }
 
 int conv_gemm_ffma_launch(const ConvGemmArgs& a, int taps, cudaStream_t stream) {
@@ -848,11 +870,20 @@ extern "C" int e3_pack_inversion_record(const float* w_plus, const float* w_dec,
   E3_REQUIRE((image == nullptr) == (target == nullptr), E3_ERR_BAD_ARG,
              "e3_pack_inversion_record: image and target come together");
   if (batch == 0) return E3_OK;
-  const int rec_len = 2304 + n_latent * 512 + 2;
-  E3_CUDA(cudaMemsetAsync(record, 0, (size_t)batch * rec_len * sizeof(float), as_stream(stream)));
-  const int parts = image ? 32 : 1;
-  pack_record_kernel<<<dim3(batch, parts), 256, 0, as_stream(stream)>>>(
-      w_plus, w_dec, n_latent, image, target, image_numel > 0 ? image_numel : 1, record);
+  const int parts = image ? RECORD_PARTS : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(parts, batch);
+  cfg.blockDim = dim3(RECORD_THREADS);
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = parts;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  E3_CUDA(cudaLaunchKernelEx(&cfg, pack_record_kernel, w_plus, w_dec, n_latent, image, target,
+                             image_numel > 0 ? image_numel : (int64_t)1, record));
   E3_CUDA(cudaGetLastError());
   return E3_OK;
 }

@@ -604,7 +604,8 @@ siren_render_kernel(const __grid_constant__ RenderArgs a) {
 }
 
 static int launch_render(const RenderArgs& a, int mode, cudaStream_t stream) {
-  static thread_local bool attr_set[2] = {false, false};
+  static thread_local bool attr_set_dev[E3_MAX_DEVICES][2] = {};  // function attributes are per device
+  bool (&attr_set)[2] = attr_set_dev[device_slot()];
   const void* fn = (mode == 0) ? (const void*)siren_render_kernel<0> : (const void*)siren_render_kernel<1>;
   if (!attr_set[mode]) {
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));

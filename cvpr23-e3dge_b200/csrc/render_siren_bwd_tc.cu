@@ -601,7 +601,8 @@ __global__ void __launch_bounds__(256) film_bwd_kernel(const float* __restrict__
 
 template <int MODE>
 int launch_bwd_variant(const RenderBwdArgs& a, cudaStream_t stream) {
-  static thread_local bool attr_set = false;
+  static thread_local bool attr_set_dev[E3_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_set_dev[device_slot()];
   const int smem_bytes = (int)sizeof(SmemBwd) + 1024;
   auto* fn = siren_render_bwd_tc_kernel<MODE>;
   if (!attr_set) {

@@ -971,7 +971,8 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 
 template <int MODE, int CL, bool STASH = false, int EPI = 0>
 static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
-  static thread_local bool attr_set = false;
+  static thread_local bool attr_set_dev[E3_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_set_dev[device_slot()];
   const int smem_bytes = (int)sizeof(SmemTC) + 1024;
   auto* fn = siren_render_tc_kernel<MODE, CL, STASH, EPI>;
   if (!attr_set) {
@@ -991,7 +992,8 @@ static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
   cfg.numAttrs = 1;
   // persistent kernel: never more CTAs than can be co-resident as whole clusters (GPCs of 16/18/20
   // SMs cannot all be tiled by clusters of 4)
-  static thread_local int max_clusters = 0;
+  static thread_local int max_clusters_dev[E3_MAX_DEVICES] = {};
+  int& max_clusters = max_clusters_dev[device_slot()];
   if (!max_clusters) {
     cfg.gridDim = dim3((sm_count() / CL) * CL);
     int n = 0;
@@ -1031,8 +1033,11 @@ static int render_cluster_size() {
 int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   if (a_in.n_tiles <= 0) return E3_OK;
   RenderArgs a = a_in;
-  if (const char* tp = getenv("E3DGE_RENDER_TRACE_PTR"))  // measurement aid, see RenderArgs::trace
-    a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
+#ifdef E3_TRACE  // measurement build only (profiles/trace_render.py): clock64 samples through a raw device pointer
+  if (const char* tp = getenv("E3DGE_RENDER_TRACE_PTR")) a.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
+#else
+  a.trace = nullptr;
+#endif
   const int cl = render_cluster_size();
   static int epi = -1;
   if (epi < 0) {

@@ -531,7 +531,8 @@ static int launch_conv_pair(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo
                             const CUtensorMap& tmB_lo, const CUtensorMap& tmOut, const ConvGemmArgs& a,
                             const TcTile& t, cudaStream_t stream) {
   auto* fn = tc_conv_pair_kernel<TAPS, NT>;
-  static thread_local bool attr_set = false;
+  static thread_local bool attr_set_dev[E3_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_set_dev[device_slot()];
   if (!attr_set) {
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NT>::kSmemBytes));
     attr_set = true;
@@ -553,7 +554,8 @@ static int launch_conv_pair(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent kernel: no more pairs than can be co-resident as clusters
-  static thread_local int max_clusters = 0;
+  static thread_local int max_clusters_dev[E3_MAX_DEVICES] = {};
+  int& max_clusters = max_clusters_dev[device_slot()];
   if (!max_clusters) {
     cfg.gridDim = dim3(2 * (sm_count() / 2));
     int n = 0;
@@ -830,7 +832,8 @@ int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, 
   if ((rc = make_tensor_map_bf16(&tmA_lo, xs_lo, 2, adims, astr, abox))) return rc;
   if ((rc = make_tensor_map_bf16(&tmB_hi, w_hi, 2, bdims, bstr, bbox))) return rc;
   if ((rc = make_tensor_map_bf16(&tmB_lo, w_lo, 2, bdims, bstr, bbox))) return rc;
-  static thread_local bool attr_set = false;
+  static thread_local bool attr_set_dev[E3_MAX_DEVICES] = {};  // function attributes are per device
+  bool& attr_set = attr_set_dev[device_slot()];
   if (!attr_set) {
     E3_CUDA(cudaFuncSetAttribute((const void*)tc_upconv_phase_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -946,7 +949,8 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
       return launch_conv_pair<9, 256>(tmA_hi, tmA_lo, pB_hi, pB_lo, tmOut, a, t, stream);
     }
   }
-  static thread_local bool attr_set[2] = {false, false};
+  static thread_local bool attr_set_dev[E3_MAX_DEVICES][2] = {};  // function attributes are per device
+  bool (&attr_set)[2] = attr_set_dev[device_slot()];
   const int which = taps == 9 ? 1 : 0;
   if (!attr_set[which]) {
     const void* fn = which ? (const void*)tc_conv_kernel<9> : (const void*)tc_conv_kernel<1>;

@@ -6,6 +6,7 @@ non-CUDA tensors.
 """
 import ctypes
 import os
+import threading
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_uint32, c_void_p)
 
@@ -116,10 +117,38 @@ _PROTOTYPES = {
 }
 
 _lib = None
+_tls = threading.local()  # device of the tensors handed to ptr() since the last C call
+
+
+class _Guarded:
+    """The ctypes handle behind a device guard.  The C side launches on the calling thread's CURRENT
+    device (SURVEY.md §8b "Threading"); tensors living on another device would otherwise be launched on the
+    wrong GPU.  `ptr()` notes the device of every tensor argument, `cur_stream()` returns that device's
+    current stream, and the call itself runs with that device current."""
+
+    def __init__(self, cdll):
+        object.__setattr__(self, "_cdll", cdll)
+        object.__setattr__(self, "_fns", {})
+
+    def __getattr__(self, name):
+        fns = object.__getattribute__(self, "_fns")
+        fn = fns.get(name)
+        if fn is None:
+            raw = getattr(object.__getattribute__(self, "_cdll"), name)
+
+            def fn(*args, _raw=raw):
+                dev = getattr(_tls, "dev", None)
+                _tls.dev = None
+                if dev is None or dev == torch.cuda.current_device():
+                    return _raw(*args)
+                with torch.cuda.device(dev):
+                    return _raw(*args)
+            fns[name] = fn
+        return fn
 
 
 def load():
-    """Loads (once) and returns the ctypes handle.  Raises if the library was not built."""
+    """Loads (once) and returns the guarded ctypes handle.  Raises if the library was not built."""
     global _lib
     if _lib is not None:
         return _lib
@@ -133,8 +162,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
-    return lib
+    _lib = _Guarded(lib)
+    return _lib
 
 
 def exported_symbols():
@@ -150,10 +179,21 @@ KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
                     "e3_styled_conv3x3_up_fwd": 3, "e3_styled_conv3x3_up_fwd_split": 3,
                     "e3_styled_conv3x3_fwd_presplit": 1, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
                     "e3_torgb_bwd": 2, "e3_modconv_styles_bwd": 1,
-                    "e3_local_feature_query": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, _fp, c_int, c_int, c_int, c_int,
-                                       c_int, c_int, _fp, _fp, _fp, _fp, _fp]),
     "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1, "e3_local_feature_query": 1}
 launch_count = 0
+
+# Packed weight images (SIREN stream, conv operands, sum_k W^2) are cached per module and keyed on
+# (data_ptr, tensor._version, pack_epoch).  In-place updates through `.data` (the reference's EMA
+# `accumulate()`, training_utils.py:40-45; Ranger's `p.data.copy_`) do not bump `_version`, so whoever
+# updates weights that way calls `invalidate_packed()` afterwards; `load_state_dict`, `.to()/.cuda()` and
+# `train()/eval()` switches do it on their own.
+pack_epoch = 0
+
+
+def invalidate_packed():
+    """Forces every packed weight image of this process to be rebuilt at its next use."""
+    global pack_epoch
+    pack_epoch += 1
 
 
 def check(rc, what="", launches=None):
@@ -163,6 +203,16 @@ def check(rc, what="", launches=None):
         msg = load().e3_last_error()
         raise RuntimeError(f"e3dge_b200 {what} failed (status {rc}): "
                            f"{msg.decode() if msg else 'no message'}")
+
+
+def _note_device(t):
+    idx = t.device.index
+    dev = getattr(_tls, "dev", None)
+    if dev is None:
+        _tls.dev = idx
+    elif dev != idx:
+        _tls.dev = None
+        raise RuntimeError(f"e3dge_b200: tensors of one call live on different devices (cuda:{dev}, cuda:{idx})")
 
 
 def ptr(t):
@@ -175,11 +225,25 @@ def ptr(t):
         raise RuntimeError(f"e3dge_b200: float32 tensor required, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError("e3dge_b200: contiguous tensor required")
+    _note_device(t)
+    return c_void_p(t.data_ptr())
+
+
+def vptr(t):
+    """Device pointer of a contiguous CUDA tensor of any dtype (bf16 operand images, strided latents)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("e3dge_b200: CUDA tensor required (this framework has no CPU path)")
+    _note_device(t)
     return c_void_p(t.data_ptr())
 
 
 def cur_stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current stream of the device the call's tensors live on (the calling thread's current device when
+    no tensor has been seen yet)."""
+    dev = getattr(_tls, "dev", None)
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def as_f32c(t):
@@ -187,3 +251,21 @@ def as_f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+_warned_frozen = set()
+
+
+def warn_if_trainable(module, what):
+    """The backward kernels return gradients for latents / features / local modulation only (the E3DGE
+    path trains encoders against a frozen generator, trainer.py:881-900): a generator parameter that still
+    has requires_grad=True would silently get no gradient, so say it once."""
+    if what in _warned_frozen:
+        return
+    names = [n for n, p in module.named_parameters() if p.requires_grad]
+    if names:
+        import warnings
+        _warned_frozen.add(what)
+        warnings.warn(f"e3dge_b200: {what} has {len(names)} parameter(s) with requires_grad=True (e.g. "
+                      f"{names[0]}); this path provides no gradients for the generator's own weights — "
+                      "freeze them (requires_grad_(False)) or expect None grads", RuntimeWarning, stacklevel=3)

@@ -37,7 +37,12 @@ class GraphedCall:
                 self.result = fn()
             self.launches = _lib.launch_count - n0
         cur.wait_stream(side)
+        self.pack_epoch = _lib.pack_epoch
 
     def __call__(self):
+        if _lib.pack_epoch != self.pack_epoch:
+            raise RuntimeError("e3dge_b200: weights were re-packed (load_state_dict / .to() / train() / "
+                               "invalidate_packed()) after this graph was recorded; the graph holds the old "
+                               "packed images — record a new GraphedCall")
         self.graph.replay()
         return self.result

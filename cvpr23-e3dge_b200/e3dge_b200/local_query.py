@@ -56,7 +56,7 @@ def query(points, calibs, im_feat=None, im_feat_nhwc=None, return_projection_onl
             raise RuntimeError("query: one feature map per image of the batch is required")
         _, h, w, c = fmap.shape
         feats = torch.empty(b, n, c, device=dev)
-    vp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    vp = _lib.vptr
     pts = points.detach()
     _lib.check(lib.e3_local_feature_query(vp(fmap), vp(pts), pts.stride(0), pts.stride(1), pts.stride(2),
                                           _lib.ptr(calibs), calibs.shape[-2] * 4, b, n, h, w, c, vp(feats), _lib.ptr(xy),

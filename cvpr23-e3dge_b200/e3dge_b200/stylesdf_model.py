@@ -130,7 +130,7 @@ class _PackedConv:
     def get(self, weight, layout):
         """layout: 0 plain / 1 upsampling forward, 2 / 3 their backward images (E3_CONV_PACK_*)."""
         layout = int(layout)
-        key = (weight.data_ptr(), weight._version, layout)
+        key = (weight.data_ptr(), weight._version, layout, _lib.pack_epoch)
         if key == self.key:
             return self.wp, self.wsq
         lib = _lib.load()
@@ -196,6 +196,7 @@ class _StyledConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, conv, x, latent, noise, noise_w, act_bias):
+        _lib.warn_if_trainable(conv, "ModulatedConv2d")
         y, saved = _styled_conv_nhwc(conv, x, latent, noise, noise_w, act_bias, want_saved=True)
         ctx.conv, ctx.saved = conv, saved
         ctx.save_for_backward(x, y)
@@ -296,6 +297,18 @@ class ModulatedConv2d(nn.Module):
         self._packed_bwd = _PackedConv()
         self._prefetched = None  # ((latent ptr, batch), s, d) left by Decoder.prepare for the next call
 
+    def _apply(self, fn, *args, **kwargs):
+        _lib.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        _lib.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        _lib.invalidate_packed()
+        return super().train(mode)
+
     def styles(self, latent):
         """s [B,cin] and (if demodulating) d [B,cout] for latent [B,512] (may be a strided
         view latent[:, i] of [B,n_latent,512])."""
@@ -313,7 +326,7 @@ class ModulatedConv2d(nn.Module):
         d = torch.empty(b, self.out_channel, device=latent.device,
                         dtype=torch.float32) if self.demodulate else None
         import ctypes
-        _lib.check(lib.e3_modconv_styles(ctypes.c_void_p(latent.data_ptr()),
+        _lib.check(lib.e3_modconv_styles(_lib.vptr(latent),
                                          latent.stride(0) if b > 1 else 512,
                                          _lib.ptr(_lib.as_f32c(self.modulation.weight.detach())),
                                          _lib.ptr(_lib.as_f32c(self.modulation.bias.detach())),
@@ -445,7 +458,7 @@ def _styled_conv_pair_nhwc(up, plain, x, lat_up, lat_plain, noise_up, noise_plai
     xs = torch.empty(2, b, oh, ow, c, device=x.device, dtype=torch.bfloat16)
     nbytes = lib.e3_styled_conv_scratch_bytes(b, h, w, cin, c, 1)
     scratch = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
-    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    vp = _lib.vptr
     f32 = lambda t: _lib.ptr(_lib.as_f32c(t.detach()))
     _lib.check(lib.e3_styled_conv3x3_up_fwd_split(
         _lib.ptr(x), _lib.ptr(wp1), _lib.ptr(s1), _lib.ptr(d1), _lib.ptr(n1), st1, f32(up.noise.weight),

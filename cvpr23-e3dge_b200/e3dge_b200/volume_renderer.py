@@ -148,7 +148,7 @@ class _PackedSiren:
         flat = []
         for v in wt.values():
             flat.extend(v if isinstance(v, list) else [v])
-        key = tuple((t.data_ptr(), t._version) for t in flat)
+        key = (_lib.pack_epoch,) + tuple((t.data_ptr(), t._version) for t in flat)
         if self.buf is not None and key == self.key:
             return self.buf
         lib = _lib.load()
@@ -214,6 +214,7 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, renderer, film, local_alpha, local_beta, cam_poses, focal, near, far, z_jitter,
                 flags_over, want_taps):
+        _lib.warn_if_trainable(renderer, "VolumeFeatureRenderer")
         local_mod = None if local_alpha is None else (local_alpha, local_beta)
         out, call = renderer._render_raw(None, cam_poses, focal, near, far, z_jitter, local_mod,
                                          flags_over, want_taps, film=film, train=True)
@@ -362,6 +363,23 @@ class VolumeFeatureRenderer(nn.Module):
         self._last_names = None
 
     # ------------------------------------------------------------------ internals
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): new storages -> new packed image
+        _lib.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        _lib.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        _lib.invalidate_packed()
+        return super().train(mode)
+
+    def invalidate_packed(self):
+        """Call after updating weights in place through `.data` (EMA `accumulate`, Ranger): such updates
+        do not bump the version counters the packed image is keyed on."""
+        _lib.invalidate_packed()
+
     @property
     def siren(self):
         return self.network.netGlobal if self.enable_local_model else self.network

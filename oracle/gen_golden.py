@@ -64,7 +64,10 @@ GEN_CASES = {
                                            spatial_super_sampling_factor=2,
                                            force_background=False), renderer_only=True),
     "full_256": dict(size=256, res=64, n_samples=24, batch=2, seed=21, variant="sharp",
-                     wplus=True, ropt={}, stride=8),
+                     wplus=True, ropt={}, stride=8, offset=3),
+    # density branch without the SDF activation (volume_renderer.py:862-867): alpha = 1-exp(-softplus(raw)*dist)
+    "small_no_sdf": dict(size=64, res=16, n_samples=24, batch=2, seed=15, variant="sharp",
+                         wplus=True, ropt=dict(no_sdf=True), renderer_only=True),
 }
 
 RENDER_KEYS = ["rays_o", "rays_d", "dists", "near", "far", "hit_prob", "points", "sdf",
@@ -86,18 +89,21 @@ def run_generator_case(ref, name, cfg):
     stride = cfg.get("stride")
     arrays = {}
     keys = RENDER_KEYS + ([] if cfg.get("renderer_only") else ["gen_imgs"])
+
+    def sub(t, k, first):
+        if k in ("features", "gen_thumb_imgs", "xyz", "gen_imgs", "mask"):  # [B,C,H,W(,1)]
+            return t[:, :, first::stride, first::stride]
+        return t[:, first::stride, first::stride]  # [B,H,W,...]
+
     for k in keys:
         t = out[k]
         arrays["sum." + k] = _checksums(t)
         if stride:
-            if k in ("features", "gen_thumb_imgs", "xyz"):  # [B,C,H,W]
-                t = t[:, :, ::stride, ::stride]
-            elif k == "gen_imgs":
-                t = t[:, :, ::stride, ::stride]
-            elif k == "mask":  # [B,1,H,W,1]
-                t = t[:, :, ::stride, ::stride]
-            else:  # [B,H,W,...]
-                t = t[:, ::stride, ::stride]
+            # a second sub-sample on an offset grid: together the two lattices touch every 128-row tile of
+            # the renderer (5 rays) and every 8x16 / 4x32 conv tile of the decoder
+            if cfg.get("offset"):
+                arrays["off." + k] = _np(sub(t, k, cfg["offset"])).astype(np.float32)
+            t = sub(t, k, 0)
         arrays[k] = _np(t).astype(np.float32)
     arrays["config"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
     return arrays

@@ -135,3 +135,97 @@ def test_config4_sdf_grid_128_cubed():
     with torch.no_grad():
         ref = O.sdf_query(sd, grid[:, idx], w)
     assert rel_linf(sdf[:, idx.cuda()].cpu(), ref) < TOL
+
+
+def test_config1_the_benched_batch_all_frames_full_tensors_through_the_graph():
+    """bench.py's own generator, its own seeded B=8 batch, through the CUDA-graph replay it times
+    (e3dge_b200.graphed.GraphedCall), every frame and every element against the oracle."""
+    import bench
+    from e3dge_b200.graphed import GraphedCall
+    dev = torch.device("cuda", torch.cuda.current_device())
+    G, sd = bench.build_generator(dev)
+    inp = bench.make_inputs(0)
+    static = {k: v.to(dev) for k, v in inp.items()}
+    assert static["w"].shape[0] == bench.BATCH == 8
+
+    def core():
+        with torch.no_grad():
+            return G([static["w"], static["w_dec"]], static["cam_poses"], static["focal"], static["near"],
+                     static["far"], input_is_latent=True, randomize_noise=False, return_xyz=True, return_sdf=True)
+    call = GraphedCall(core)
+    out = call()
+    torch.cuda.synchronize()
+    got = {k: out[k].cpu() for k in ("features", "gen_thumb_imgs", "sdf", "hit_prob", "xyz", "depth", "gen_imgs")}
+    torch.set_num_threads(max(1, min(16, torch.get_num_threads())))
+    with torch.no_grad():
+        ref = O.generator_forward(sd, inp["w"], inp["w_dec"], inp["cam_poses"], inp["focal"], inp["near"],
+                                  inp["far"], res=bench.RES, n_samples=bench.N_SAMPLES)
+    for k, t in got.items():
+        assert t.shape == ref[k].shape, k
+        for b in range(bench.BATCH):  # per frame: a frame with small values cannot hide behind a bright one
+            err = rel_linf(t[b], ref[k][b])
+            assert err < TOL, f"frame {b} {k}: rel-Linf {err:.3e}"
+    # the replay is the eager pass, bit for bit
+    eager = core()
+    for k in got:
+        assert torch.equal(eager[k], out[k]), k
+
+
+def test_size_1024_generator_full_frame():
+    """The shipped scripts run --size 1024 (demo_view_synthesis.sh:35-36): 64^2 features -> 4 up-sampling stages
+    down to 32 channels at 1024^2 (stylesdf_model.py:614-624).  One full frame, every pixel, against the oracle."""
+    size, res, S, seed = 1024, 64, 24, 304
+    G, sd = _build(size, res, seed, S)
+    sd = synthetic_state_dict(size, res, seed, "sharp")
+    G.load_state_dict(sd, strict=True)
+    inp = P.make_inputs(seed, 1, decoder_layout(size, res), res)
+    d = {k: v.cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        out = G([d["w"], d["w_dec"]], d["cam_poses"], d["focal"], d["near"], d["far"], input_is_latent=True,
+                randomize_noise=False, return_xyz=True, return_sdf=True)
+        ref = O.generator_forward(sd, inp["w"], inp["w_dec"], inp["cam_poses"], inp["focal"], inp["near"],
+                                  inp["far"], res=res, n_samples=S)
+    assert out["gen_imgs"].shape == (1, 3, size, size)
+    for k in ("features", "gen_thumb_imgs", "sdf", "hit_prob", "gen_imgs"):
+        err = rel_linf(out[k].cpu(), ref[k])
+        assert err < TOL, f"{k}: rel-Linf {err:.3e}"
+
+
+def test_perturbed_samples_match_the_oracle_on_the_same_depths():
+    """perturb > 0 (training, volume_renderer.py:1213-1228): the jittered depths are drawn on the device and
+    handed to the kernel explicitly; the oracle's network + composite on those very depths must agree."""
+    size, res, S, seed = 64, 16, 24, 305
+    from e3dge_b200 import model_options, rendering_options
+    from e3dge_b200.stylesdf_model import G_pred_latents
+    sd = synthetic_state_dict(size, res, seed, "sharp")
+    G = G_pred_latents(model_options(size=size, renderer_spatial_output_dim=res),
+                       rendering_options(N_samples=S, perturb=1.0), full_pipeline=False).eval()
+    G.load_state_dict(sd, strict=False)
+    G = G.cuda()
+    R = G.renderer
+    R.test, R.perturb = False, 1.0
+    inp = P.make_inputs(seed, 2, 1, res)
+    d = {k: v.cuda() for k, v in inp.items()}
+    torch.manual_seed(seed)
+    zj = R._make_z_jitter(d["near"], d["far"], 2, d["w"].device)
+    with torch.no_grad():
+        o = R._render_raw(d["w"], d["cam_poses"], d["focal"], d["near"], d["far"], z_jitter=zj)
+    z = zj.cpu()
+    # stratified offsets stay inside their own bins, one offset per ray with offset sampling
+    near, far = inp["near"].reshape(-1, 1, 1, 1), inp["far"].reshape(-1, 1, 1, 1)
+    step = (far - near) / S
+    assert (z[..., 1:] > z[..., :-1]).all() and (z >= near).all() and (z <= far).all()
+    assert ((z[..., 1:] - z[..., :-1]) - step).abs().max().item() < 1e-6
+    rays_o, rays_d, viewdirs = O.get_rays(inp["focal"], inp["cam_poses"], res)
+    viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+    pts = rays_o.unsqueeze(3) + rays_d.unsqueeze(3) * z.unsqueeze(-1)
+    with torch.no_grad():
+        raw = O.run_network(pts, viewdirs, inp["w"], sd)
+        vi = O.volume_integration(raw, z, rays_d, pts, sd["renderer.sigmoid_beta"])
+    assert rel_linf(o["points"].cpu(), pts) < 1e-5
+    assert rel_linf(o["sdf"].cpu(), vi["sdf"]) < TOL
+    assert rel_linf(o["hit_prob"].cpu(), vi["weights"]) < TOL
+    assert rel_linf(o["dists"].cpu(), vi["dists"]) < TOL
+    assert rel_linf(o["features"].cpu(), vi["feature_map"].permute(0, 3, 1, 2)) < TOL
+    assert rel_linf(o["gen_thumb_imgs"].cpu(), vi["rgb_map"].permute(0, 3, 1, 2)) < TOL
+    assert rel_linf(o["xyz"].cpu(), vi["xyz"].permute(0, 3, 1, 2)) < TOL

@@ -14,15 +14,15 @@ from helpers import load_golden, rel_linf, synthetic_state_dict, decoder_layout
 TOL = 2e-5
 
 GEN_CASES = ["small_wplus", "small_sharp_w", "small_s18_rayd_viewdirs",
-             "small_stratified_ss2", "full_256"]
+             "small_stratified_ss2", "full_256", "small_no_sdf"]
 
 
-def _sub(t, k, stride):
+def _sub(t, k, stride, first=0):
     if not stride:
         return t
     if k in ("features", "gen_thumb_imgs", "xyz", "gen_imgs", "mask"):
-        return t[:, :, ::stride, ::stride]
-    return t[:, ::stride, ::stride]
+        return t[:, :, first::stride, first::stride]
+    return t[:, first::stride, first::stride]
 
 
 @pytest.mark.parametrize("name", GEN_CASES)
@@ -37,7 +37,8 @@ def test_generator_cases(name):
               spatial_ss=ro.get("spatial_super_sampling_factor", 1),
               static_viewdirs=ro.get("static_viewdirs", True),
               offset_sampling=not ro.get("no_offset_sampling", False),
-              force_background=ro.get("force_background", True))
+              force_background=ro.get("force_background", True),
+              with_sdf=not ro.get("no_sdf", False))
     with torch.no_grad():
         if cfg.get("renderer_only"):
             out = O.renderer_forward(sd, inp["cam_poses"], inp["focal"], inp["near"],
@@ -53,7 +54,10 @@ def test_generator_cases(name):
             got = np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
             np.testing.assert_allclose(got[1:], g[1:], rtol=1e-5, err_msg=k)
             continue
-        got = _sub(out[k], k, stride)
+        if k.startswith("off."):  # second sub-sample lattice, offset by cfg["offset"]
+            got, k = _sub(out[k[4:]], k[4:], stride, cfg["offset"]), k
+        else:
+            got = _sub(out[k], k, stride)
         assert tuple(got.shape) == g.shape, (k, got.shape, g.shape)
         err = rel_linf(got, g)
         assert err < TOL, f"{name}:{k} rel-Linf {err:.3e}"
