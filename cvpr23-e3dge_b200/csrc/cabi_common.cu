@@ -67,5 +67,5 @@ extern "C" int e3_ffma_peak_probe(int iters, float* sink, void* stream) {
   return E3_OK;
 }
 
-extern "C" int e3_abi_version(void) { return 3; }
+extern "C" int e3_abi_version(void) { return 4; }
 extern "C" const char* e3_last_error(void) { return e3::g_last_error; }

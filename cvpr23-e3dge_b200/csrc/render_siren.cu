@@ -689,7 +689,8 @@ extern "C" int e3_render_fwd(const void* packed, const e3_render_params* p, cons
 static int siren_points_fwd_impl(const void* packed, const float* film, const float* points,
                                  const float* viewdirs, int batch, int n_points, float pts_scale,
                                  float* sdf, float* raw_rgb, float* feat, uint32_t flags, float* stash,
-                                 void* stream) {
+                                 void* stream, const float* local_alpha = nullptr, const float* local_beta = nullptr,
+                                 float* h8 = nullptr) {
   E3_REQUIRE(batch >= 0 && n_points >= 0, E3_ERR_BAD_ARG, "e3_siren_points_fwd: negative size");
   if (batch == 0 || n_points == 0) return E3_OK;
   E3_REQUIRE(packed && film && points && sdf, E3_ERR_BAD_ARG, "e3_siren_points_fwd: null argument");
@@ -705,7 +706,14 @@ static int siren_points_fwd_impl(const void* packed, const float* film, const fl
   a.p_sdf = sdf;
   a.p_rgb = raw_rgb;
   a.p_feat = feat;
+  a.p_h8 = h8;
+  a.in.local_alpha = local_alpha;
+  a.in.local_beta = local_beta;
   const bool ffma = (flags & E3_RENDER_FP32_CUDA_CORES) != 0;
+  E3_REQUIRE(!(ffma && (h8 || local_alpha)), E3_ERR_UNSUPPORTED,
+             "e3_siren_points_fwd_ex: backbone features / local modulation need the tensor-core kernel");
+  E3_REQUIRE((local_alpha == nullptr) == (local_beta == nullptr), E3_ERR_BAD_ARG,
+             "e3_siren_points_fwd_ex: local_alpha and local_beta come together");
   const int tile_m = ffma ? TILE_M : 128;
   a.rays_per_tile = tile_m;
   a.tiles_per_image = (n_points + tile_m - 1) / tile_m;
@@ -721,6 +729,14 @@ extern "C" int e3_siren_points_fwd(const void* packed, const float* film, const 
                                    void* stream) {
   return siren_points_fwd_impl(packed, film, points, viewdirs, batch, n_points, pts_scale, sdf, raw_rgb, feat,
                                flags, nullptr, stream);
+}
+
+extern "C" int e3_siren_points_fwd_ex(const void* packed, const float* film, const float* points,
+                                      const float* viewdirs, int batch, int n_points, float pts_scale,
+                                      const float* local_alpha, const float* local_beta, float* sdf,
+                                      float* raw_rgb, float* feat, float* h8, uint32_t flags, void* stream) {
+  return siren_points_fwd_impl(packed, film, points, viewdirs, batch, n_points, pts_scale, sdf, raw_rgb, feat,
+                               flags, nullptr, stream, local_alpha, local_beta, h8);
 }
 
 extern "C" int e3_siren_points_fwd_train(const void* packed, const float* film, const float* points,

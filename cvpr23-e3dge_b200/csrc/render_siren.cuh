@@ -72,6 +72,7 @@ struct RenderArgs {
   float* p_sdf;
   float* p_rgb;
   float* p_feat;
+  float* p_h8;    // explicit-points mode, optional: backbone features (layer-8 output before the local modulation) [B,N,256]
   int with_view;  // 0: stop after the sdf head (sdf-only query)
   float* stash;   // NULL, or [n_tiles][9][256][128] pre-sin phases for e3_render_bwd (tensor-core kernel)
   // measurement aid (profiles/trace_render.py): when non-null, CTA 0 records clock64() stamps of the

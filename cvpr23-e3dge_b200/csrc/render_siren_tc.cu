@@ -629,7 +629,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         const bool feed = !last || a.with_view;
         const float* la = nullptr;
         const float* lb = nullptr;
-        if (MODE == 0 && last && a.in.local_alpha && valid) {
+        if (last && a.in.local_alpha && valid) {  // [B,H,W,S,256] / explicit points [B,N,256]
           la = a.in.local_alpha + (samp0 + m) * SW;
           lb = a.in.local_beta + (samp0 + m) * SW;
         }
@@ -641,6 +641,11 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             // sdf head sees the un-modulated h8 (volume_renderer.py:206-208, 217-220)
 #pragma unroll
             for (int i = 0; i < 8; ++i) sdf_acc = fmaf(sm.wsig[n0 + i], v[i], sdf_acc);
+            if (MODE == 1 && a.p_h8 && valid) {  // SirenGenerator.forward_generator's output (volume_renderer.py:168-194)
+              float4* dst = reinterpret_cast<float4*>(a.p_h8 + (samp0 + m) * SW + n0);
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
             if (la) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)

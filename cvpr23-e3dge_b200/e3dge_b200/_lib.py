@@ -24,6 +24,13 @@ class SirenWeights(Structure):
                 ("rgb_w", _fp), ("rgb_b", _fp), ("sigma_w", _fp), ("sigma_b", _fp)]
 
 
+class LocalMlpWeights(Structure):
+    _fields_ = [(n, _fp) for n in ("enc_fc0_w", "enc_fc0_b", "enc_fc1_w", "enc_fc1_b", "enc_shortcut_w",
+                                   "scale0_w", "scale0_b", "scale2_w", "scale2_b",
+                                   "shift0_w", "shift0_b", "shift2_w", "shift2_b",
+                                   "tex_fc0_w", "tex_fc0_b", "tex_fc1_w", "tex_fc1_b", "tex_shortcut_w")]
+
+
 class RenderParams(Structure):
     _fields_ = [("batch", c_int32), ("height", c_int32), ("width", c_int32), ("res", c_int32),
                 ("n_samples", c_int32), ("flags", c_uint32), ("pts_scale", c_float),
@@ -71,6 +78,8 @@ _PROTOTYPES = {
                               POINTER(RenderOutputs), _fp]),
     "e3_siren_points_fwd": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, c_uint32,
                                     _fp]),
+    "e3_siren_points_fwd_ex": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, _fp, _fp, _fp,
+                                       c_uint32, _fp]),
     "e3_siren_points_fwd_train": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_float, _fp, _fp, _fp, _fp,
                                           _fp]),
     "e3_render_stash_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -111,6 +120,10 @@ _PROTOTYPES = {
     "e3_torgb_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, _fp, c_int, c_int, c_int, c_int, _fp]),
     "e3_local_feature_query": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, _fp, c_int, c_int, c_int, c_int,
                                        c_int, c_int, _fp, _fp, _fp, _fp, _fp]),
+    "e3_local_mlp_packed_bytes": (c_size_t, []),
+    "e3_local_mlp_pack": (c_int, [POINTER(LocalMlpWeights), _fp, _fp]),
+    "e3_local_mlp_workspace_bytes": (c_size_t, [c_int64]),
+    "e3_local_mlp_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, c_size_t, _fp]),
     "e3_pack_inversion_record": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int64, _fp, _fp]),
     "e3_ffma_peak_probe": (c_int, [c_int, _fp, _fp]),
     "e3_ffma_peak_probe_sink_floats": (c_size_t, []),
@@ -172,14 +185,15 @@ def exported_symbols():
 
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches)
 KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
-                    "e3_siren_points_fwd": 1, "e3_siren_points_fwd_train": 1, "e3_render_bwd": 3,
+                    "e3_siren_points_fwd": 1, "e3_siren_points_fwd_ex": 1, "e3_siren_points_fwd_train": 1, "e3_render_bwd": 3,
                     "e3_siren_points_bwd": 3, "e3_film_bwd": 1, "e3_fused_bias_act": 1, "e3_upfirdn2d": 1,
                     "e3_modconv_weight_sq": 1, "e3_modconv_styles": 2, "e3_nchw_to_nhwc": 1,
                     "e3_nhwc_to_nchw": 1, "e3_conv_pack_weight": 1, "e3_styled_conv3x3_fwd": 2,
                     "e3_styled_conv3x3_up_fwd": 3, "e3_styled_conv3x3_up_fwd_split": 3,
                     "e3_styled_conv3x3_fwd_presplit": 1, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
                     "e3_torgb_bwd": 2, "e3_modconv_styles_bwd": 1,
-    "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1, "e3_local_feature_query": 1}
+    "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1, "e3_local_feature_query": 1,
+                    "e3_local_mlp_pack": 19, "e3_local_mlp_fwd": 7}
 launch_count = 0
 
 # Packed weight images (SIREN stream, conv operands, sum_k W^2) are cached per module and keyed on

@@ -6,9 +6,10 @@ its runners can call this module unchanged; the arithmetic between `forward()` a
 returned dict is ONE CUDA kernel (csrc/render_siren.cu) instead of ~150 ATen launches.
 
 Not provided (SURVEY.md §8 out of scope / "next" rows): marching-cubes mesh extraction
-(`return_mesh`), the PIFu `netLocal` network itself (its output enters here as an explicit
-(alpha, beta) texture modulation), second-order gradients (the eikonal terms are returned
-as values of the backward kernel, without a graph of their own).
+(`return_mesh`), the 2-D hourglass image filter of the PIFu `netLocal` (an encoder; its per-sample
+half — feature query, SFT fusion, positional encoding, texture-modulation MLP — is local_query.py /
+local_branch.py), second-order gradients (the eikonal terms are returned as values of the backward
+kernel, without a graph of their own).
 
 Training (encoders against the frozen generator, trainer.py:881-900, generator frozen at :1569): `_FilmFn`, `_RenderFn`
 and `_PointsFn` bind e3_film_bwd / e3_render_bwd / e3_siren_points_bwd, so gradients reach the
@@ -120,19 +121,184 @@ class SirenGenerator(nn.Module):
                     rgb_b=self.rgb_linear.bias, sigma_w=self.sigma_linear.weight,
                     sigma_b=self.sigma_linear.bias)
 
+    # ---- kernel plumbing ----
+    def packed_weights(self):
+        holder = self.__dict__.setdefault("_e3_packed", _PackedSiren())
+        return holder.get(self)
+
+    def film(self, styles):
+        """styles [B,256] (w) / [B,9,256] (w+) -> FiLM table [B,9,3,256] (gamma, beta, beta' = gamma*b + beta)."""
+        lib = _lib.load()
+        styles = _lib.as_f32c(styles)
+        if styles.ndim == 2:
+            b, spi = styles.shape[0], 1
+        elif styles.ndim == 3 and styles.shape[1] == 9:
+            b, spi = styles.shape[0], 9
+        else:
+            raise RuntimeError(f"styles must be [B,256] (w) or [B,9,256] (w+), got {tuple(styles.shape)}")
+        film = torch.empty(b, 9, 3, 256, device=styles.device, dtype=torch.float32)
+        _lib.check(lib.e3_film_fwd(_lib.ptr(self.packed_weights()), _lib.ptr(styles), b, spi,
+                                   _lib.ptr(film), _lib.cur_stream()), "e3_film_fwd")
+        return film
+
+    def _points(self, x, views, styles, local_mod=None, want=("sdf", "rgb", "feat"), scale=1.0):
+        """One e3_siren_points_fwd_ex launch over network inputs x [B,...,3] (already box-normalised when
+        scale == 1): any of sdf [B,...,1], rgb [B,...,3], feat [B,...,256], h8 [B,...,256]."""
+        lib = _lib.load()
+        shp = tuple(x.shape[:-1])
+        B = shp[0]
+        pts = _lib.as_f32c(x.detach()).reshape(B, -1, 3)
+        N = pts.shape[1]
+        dev = pts.device
+        with_view = "rgb" in want or "feat" in want
+        vd = None
+        if views is not None and with_view:
+            vd = _lib.as_f32c(views.detach()).expand(*shp, 3).reshape(B, -1, 3).contiguous()
+        new = lambda c: torch.empty(B, N, c, device=dev, dtype=torch.float32)
+        sdf = torch.empty(B, N, device=dev, dtype=torch.float32)
+        rgb = new(3) if with_view else None
+        feat = new(256) if with_view else None
+        h8 = new(256) if "h8" in want else None
+        la = lb = None
+        if local_mod is not None:
+            la, lb = (_lib.as_f32c(t.detach()).reshape(B, N, 256) for t in local_mod)
+        film = self.film(styles.detach())
+        _lib.check(lib.e3_siren_points_fwd_ex(
+            _lib.ptr(self.packed_weights()), _lib.ptr(film), _lib.ptr(pts), _lib.ptr(vd), B, N,
+            float(scale), _lib.ptr(la), _lib.ptr(lb), _lib.ptr(sdf), _lib.ptr(rgb), _lib.ptr(feat), _lib.ptr(h8), 0,
+            _lib.cur_stream()), "e3_siren_points_fwd_ex")
+        out = {"sdf": sdf.reshape(*shp, 1)}
+        if with_view:
+            out.update(rgb=rgb.reshape(*shp, 3), feat=feat.reshape(*shp, 256))
+        if h8 is not None:
+            out["h8"] = h8.reshape(*shp, 256)
+        return out
+
+    # ---- the reference's network-level API (inference; volume_renderer.py:168-264) ----
+    @torch.no_grad()
+    def forward_generator(self, input_pts, styles, conditions=None):
+        """Backbone features after the eight FiLM layers, [...,256] (:168-194)."""
+        return self._points(input_pts, None, styles, want=("h8",))["h8"]
+
+    forward_backbone = forward_generator  # older name of the same method (:196-204)
+
+    def forward_geo(self, feats):
+        """sdf head on given backbone features (:206-208)."""
+        return self.sigma_linear(feats)
+
+    def forward_tex(self, mlp_out, input_views, styles, conditions=None):
+        """View layer + rgb head on given backbone features, optional local texture modulation (:210-238).
+        Stand-alone PyTorch (FiLMSiren.forward); the renderer runs this inside the fused kernel."""
+        if isinstance(mlp_out, dict):
+            conditions = mlp_out.get("conditions", conditions)
+            mlp_out = mlp_out["mlp_out"]
+        if conditions and "tex" in conditions:
+            alpha, beta = conditions["tex"]
+            mlp_out = (alpha + 1) * mlp_out + beta
+        w = styles[:, -1] if styles.ndim == 3 else styles
+        out_features = self.views_linears(torch.cat([mlp_out, input_views.expand(*mlp_out.shape[:-1], 3)], -1), w)
+        return self.rgb_linear(out_features), out_features
+
+    @torch.no_grad()
+    def forward(self, x, styles, local_modulation=None):
+        """raw = [rgb | sdf | features] at network inputs x = [normalised point | view direction] (:240-264)."""
+        o = self._points(x[..., :3], x[..., 3:6], styles, local_mod=local_modulation)
+        return torch.cat([o["rgb"], o["sdf"], o["feat"]], -1)
+
 
 class SirenLocalGlobal(nn.Module):
-    """Container giving the `netGlobal.*` state_dict names of the local-branch checkpoints
-    (volume_renderer.py:267-290, train_setup.py:245-260).  `netLocal` (vendored PIFu) is
-    out of scope; callers hand its texture modulation to the renderer explicitly."""
+    """Global FiLM-SIREN + local branch — volume_renderer.py:267-558.  `netGlobal.*` / `netLocal.*` give the
+    state_dict names of the local-branch checkpoints (train_setup.py:245-260); both are reached from outside
+    (trainer.py:1611, e3dge_full_runner.py:166, 219).  `forward` is the fused route (texture modulation from
+    e3_local_mlp_fwd handed to e3_siren_points_fwd_ex); the three stage methods the reference composes it
+    from are provided with the same dict contracts."""
 
     def __init__(self, opt=None, D=8, W=256, style_dim=256, input_ch=3, input_ch_views=3,
                  output_ch=4, output_features=True, scene_scale=0.12, local_options=None, **kw):
         super().__init__()
+        from .local_branch import LocalBranch
         self.opt = opt
         self.netGlobal = SirenGenerator(opt, D, W, style_dim, input_ch, input_ch_views, output_ch,
                                         output_features, scene_scale)
-        self.netLocal = None
+        self.netLocal = LocalBranch(opt)
+
+    def forward_local(self, data_batch):
+        """:439-476 — local features of the sample points: given (`feats`) or queried from filtered images."""
+        if data_batch.get("feats") is not None:
+            return data_batch
+        points, images, calibs = (data_batch[k] for k in ("world_space_pts", "gen_imgs", "calibs"))
+        shp = points.shape
+        self.netLocal.filter(images)
+        q = self.netLocal.query(points=points.reshape(shp[0], -1, 3).permute(0, 2, 1), calibs=calibs,
+                                feat_key="ref_view", return_feat_only=True)
+        out = dict(q)
+        out["feats"] = q["feats"].permute(0, 2, 1).reshape(*shp[:-1], -1)
+        return out
+
+    def _tex_conditions(self, local_output):
+        from .local_branch import ResnetBlockFC, tex_modulation
+        tex = self.netLocal.local_feat_to_tex_modulations_linear
+        feats = local_output["feats"]
+        fused = (isinstance(tex, ResnetBlockFC) and (tex.size_in, tex.size_out) == (301, 512) and feats.is_cuda
+                 and not VolumeFeatureRenderer._wants_grad(feats, *tex.parameters()))
+        if fused:  # inference: stages 5-6 of e3_local_mlp_fwd
+            return list(tex_modulation(tex, feats))
+        return list(torch.split(tex(feats), 256, dim=-1))  # training / a caller's own module: autograd path
+
+    def forward_backbone(self, input_pts, styles, local_data_batch):
+        """:313-369."""
+        conditions = {}
+        local_output = None
+        if local_data_batch is not None and "sampling" not in local_data_batch:
+            local_output = self.forward_local(local_data_batch)
+            if getattr(self.opt, "L_pred_tex_modulations", False):
+                conditions["tex"] = self._tex_conditions(local_output)
+                local_output["tex_modulate_conditions"] = True
+        global_feats = self.netGlobal.forward_generator(input_pts, styles, conditions)
+        return dict(global_output={"feats": global_feats}, local_output=local_output,
+                    local_modulation_conditions=conditions)
+
+    def retrieve_feats_for_rendering(self, forward_out, sample_mode):
+        """:371-428 (strategies of the shipped configuration: geometry 'global', texture 'global_local')."""
+        global_feats = forward_out["global_output"]["feats"]
+        if forward_out["local_output"] is None or sample_mode:
+            return dict(feats_to_geo=global_feats, feats_to_tex=global_feats)
+        geo = getattr(self.opt, "geo_predictition_strategy", "global")
+        tex = getattr(self.opt, "tex_predictition_strategy", "global_local")
+        if "global" not in geo or "global" not in tex:
+            raise NotImplementedError("local-only prediction strategies are not adopted in the paper (:401, 414)")
+        feats_to_geo = global_feats
+        conditions = forward_out.get("local_modulation_conditions") or {}
+        if "local" in geo:
+            alpha, beta = conditions["geo"]
+            feats_to_geo = (alpha + 1) * feats_to_geo + beta
+        feats_to_tex = dict(mlp_out=global_feats)
+        if "tex" in conditions:
+            feats_to_tex["conditions"] = conditions
+        return dict(feats_to_geo=feats_to_geo, feats_to_tex=feats_to_tex)
+
+    def forward_rendering(self, feats_for_render_dict, input_views, styles):
+        """:478-517."""
+        rgb, out_features = self.netGlobal.forward_tex(feats_for_render_dict["feats_to_tex"], input_views, styles)
+        sdf = self.netGlobal.forward_geo(feats_for_render_dict["feats_to_geo"])
+        outputs = torch.cat([rgb, sdf], -1)
+        return torch.cat([outputs, out_features], -1) if self.netGlobal.output_features else outputs
+
+    def feats_to_geo_query(self, *args):
+        return self.netGlobal.forward_geo(*args)
+
+    def feats_to_tex_query(self, *args, **kwargs):
+        return self.netGlobal.forward_tex(*args, **kwargs)
+
+    @torch.no_grad()
+    def forward(self, net_inputs, styles, local_data_batch=None, sample_mode=False):
+        """:527-558, fused: (alpha, beta) from the local features, then ONE kernel for backbone, sdf head,
+        modulation, view layer and rgb head."""
+        mod = None
+        if (local_data_batch is not None and "sampling" not in local_data_batch and not sample_mode
+                and getattr(self.opt, "L_pred_tex_modulations", False)):
+            mod = tuple(self._tex_conditions(self.forward_local(local_data_batch)))
+        return self.netGlobal(net_inputs, styles, local_modulation=mod)
 
 
 class _PackedSiren:
@@ -359,7 +525,6 @@ class VolumeFeatureRenderer(nn.Module):
         # arithmetic of the 256x256 hidden layers: "tensor_cores" (tcgen05 split-bf16, default) or
         # "fp32" (exact-fp32 FFMA kernel) — include/e3dge_b200.h E3_RENDER_FP32_CUDA_CORES
         self.backend = "tensor_cores"
-        self._packed = _PackedSiren()
         self._last_names = None
 
     # ------------------------------------------------------------------ internals
@@ -385,21 +550,10 @@ class VolumeFeatureRenderer(nn.Module):
         return self.network.netGlobal if self.enable_local_model else self.network
 
     def packed_weights(self):
-        return self._packed.get(self.siren)
+        return self.siren.packed_weights()
 
     def _film(self, styles):
-        lib = _lib.load()
-        styles = _lib.as_f32c(styles)
-        if styles.ndim == 2:
-            b, spi = styles.shape[0], 1
-        elif styles.ndim == 3 and styles.shape[1] == 9:
-            b, spi = styles.shape[0], 9
-        else:
-            raise RuntimeError(f"styles must be [B,256] (w) or [B,9,256] (w+), got {tuple(styles.shape)}")
-        film = torch.empty(b, 9, 3, 256, device=styles.device, dtype=torch.float32)
-        _lib.check(lib.e3_film_fwd(_lib.ptr(self.packed_weights()), _lib.ptr(styles), b, spi,
-                                   _lib.ptr(film), _lib.cur_stream()), "e3_film_fwd")
-        return film
+        return self.siren.film(styles)
 
     def _point_flags(self):
         return _lib.RENDER_FP32_CUDA_CORES if self.backend == "fp32" else 0
@@ -676,15 +830,19 @@ class VolumeFeatureRenderer(nn.Module):
         self.local_batch = local_data_batch if self.enable_local_model else None
         if local_data_batch is not None and "tex_modulation" in local_data_batch:
             kwargs.setdefault("local_tex_modulation", local_data_batch["tex_modulation"])
-        elif (local_data_batch is not None and "feats" in local_data_batch and not sample_mode
-              and getattr(self.network, "netLocal", None) is not None):
-            # SirenLocalGlobal.forward_backbone (volume_renderer.py:323-336): the caller's netLocal maps
-            # the per-sample local features [B,H,W,S,301] to the texture modulation (alpha | beta)
-            if getattr(self.opt, "L_pred_geo_modulations", False):
-                raise NotImplementedError("geometry modulation of the local branch (volume_renderer.py:338-345) "
-                                          "is not built; the shipped scripts use texture modulation only")
-            mods = self.network.netLocal.local_feat_to_tex_modulations_linear(local_data_batch["feats"])
-            kwargs.setdefault("local_tex_modulation", tuple(torch.split(mods, 256, dim=-1)))
+        elif (local_data_batch is not None and local_data_batch.get("feats") is not None and not sample_mode
+              and getattr(self.network, "netLocal", None) is not None
+              and getattr(self.opt, "L_pred_tex_modulations", True)):
+            # SirenLocalGlobal.forward_backbone (volume_renderer.py:323-336): netLocal maps the per-sample local
+            # features [B,H,W,S,301] to the texture modulation (alpha | beta) — stages 5-6 of e3_local_mlp_fwd
+            # at inference, the module's own autograd-capable forward when it is being trained
+            net_local = self.network.netLocal
+            if hasattr(self.network, "_tex_conditions") and hasattr(net_local, "local_feat_to_tex_modulations_linear"):
+                mods = tuple(self.network._tex_conditions(local_data_batch))
+            else:  # a caller-supplied netLocal
+                mods = tuple(torch.split(net_local.local_feat_to_tex_modulations_linear(local_data_batch["feats"]),
+                                         256, dim=-1))
+            kwargs.setdefault("local_tex_modulation", mods)
         out = self.render(focal, c2w=cam_poses, near=near, far=far, styles=styles,
                           return_eikonal=return_eikonal,
                           return_surface_eikonal=return_surface_eikonal, return_mesh=return_mesh,

@@ -36,7 +36,8 @@ extern "C" {
 #define E3_SIREN_DEPTH 8   /* rendering.depth */
 #define E3_STYLE_DIM 256   /* model.style_dim */
 
-/* 3 = adds e3_styled_conv_pair_fusable / e3_styled_conv3x3_up_fwd_split / e3_styled_conv3x3_fwd_presplit and
+/* 4 = adds the local branch's per-sample MLP tail (e3_local_mlp_*); nothing of ABI 3 changed.
+ * 3 = adds e3_styled_conv_pair_fusable / e3_styled_conv3x3_up_fwd_split / e3_styled_conv3x3_fwd_presplit and
  * e3_local_feature_query; the bf16 part of the up-conv weight image (e3_conv_pack_weight layout 1) is ordered
  * by output parity phase.  Images packed by an ABI-2 library must be re-packed. */
 int e3_abi_version(void);
@@ -155,6 +156,16 @@ int e3_render_fwd(const void* packed, const e3_render_params* p, const e3_render
 int e3_siren_points_fwd(const void* packed, const float* film, const float* points,
                         const float* viewdirs, int batch, int n_points, float pts_scale,
                         float* sdf, float* raw_rgb, float* feat, uint32_t flags, void* stream);
+/* e3_siren_points_fwd with the two extras SirenLocalGlobal needs (volume_renderer.py:313-369, 515-517):
+ * local_alpha / local_beta [B,N,256] (both or neither): the local branch's texture modulation
+ * h8' = (alpha + 1) h8 + beta, applied after the sdf head and before the view layer;
+ * h8 [B,N,256] (optional output): the backbone features `forward_generator` returns.
+ * Tensor-core kernel only (E3_ERR_UNSUPPORTED with E3_RENDER_FP32_CUDA_CORES). */
+int e3_siren_points_fwd_ex(const void* packed, const float* film, const float* points,
+                           const float* viewdirs, int batch, int n_points, float pts_scale,
+                           const float* local_alpha, const float* local_beta, float* sdf,
+                           float* raw_rgb, float* feat, float* h8, uint32_t flags, void* stream);
+
 /* Same, additionally writing the backward stash (e3_render_stash_bytes(1, n_points, batch) bytes)
  * for e3_siren_points_bwd.  Tensor-core arithmetic only. */
 int e3_siren_points_fwd_train(const void* packed, const float* film, const float* points,
@@ -409,6 +420,43 @@ int e3_local_feature_query(const float* feat_nhwc, const float* points, int64_t 
                            int calib_stride, int batch, int n_points, int h, int w, int c,
                            float* feats, float* proj_xy, float* depth, unsigned char* in_img,
                            void* stream);
+
+/* ----------------------------------------------------------------------------------
+ * Local branch, rest of SURVEY.md section 8(f) row 1: the per-sample MLP tail between the feature query
+ * and the renderer's texture modulation — `Fuse_sft_MLP(257, 256)` of the runner
+ * (project/models/helper_modules/sft.py:84-109, built at e3dge_full_runner.py:301-303, called at :289-290),
+ * `PosEncoding(3, N_freqs=7)` of the sample position (project/utils/misc_utils.py:148-184,
+ * e3dge_full_runner.py:260, 293-294) and netLocal's `local_feat_to_tex_modulations_linear` =
+ * `ResnetBlockFC(301, 512)` (project/models/helper_modules/resnetfc.py:10-62,
+ * vendor/pifu/lib/model/HGPIFuGANNetResidualInputResnetFC.py:84-86), split into (alpha, beta) as
+ * SirenLocalGlobal.forward_backbone does (project/utils/volume_renderer.py:327-336).
+ * 989 161 MACs per sample on the tensor cores (tcgen05, split-bf16 operands, fp32 accumulation).
+ * Weight pointers are the reference's nn.Linear tensors ([out, in] row-major, fp32). */
+typedef struct e3_local_mlp_weights {
+  const float *enc_fc0_w, *enc_fc0_b;   /* fuse.encode_enc.fc_0   [256,513], [256] */
+  const float *enc_fc1_w, *enc_fc1_b;   /* fuse.encode_enc.fc_1   [256,256], [256] */
+  const float* enc_shortcut_w;          /* fuse.encode_enc.shortcut [256,513] (no bias) */
+  const float *scale0_w, *scale0_b, *scale2_w, *scale2_b; /* fuse.scale.{0,2} [256,256], [256] */
+  const float *shift0_w, *shift0_b, *shift2_w, *shift2_b; /* fuse.shift.{0,2} */
+  const float *tex_fc0_w, *tex_fc0_b;   /* local_feat_to_tex_modulations_linear.fc_0 [301,301], [301] */
+  const float *tex_fc1_w, *tex_fc1_b;   /* ....fc_1 [512,301], [512] */
+  const float* tex_shortcut_w;          /* ....shortcut [512,301] */
+} e3_local_mlp_weights;
+
+size_t e3_local_mlp_packed_bytes(void);
+/* weights -> packed operand image (bf16 hi / lo planes per GEMM stage, zero padded, + fp32 biases) */
+int e3_local_mlp_pack(const e3_local_mlp_weights* w, void* packed, void* stream);
+/* workspace for `rows` samples in one pass; a smaller workspace (>= the size for 128 rows) makes
+ * e3_local_mlp_fwd walk the rows in chunks */
+size_t e3_local_mlp_workspace_bytes(int64_t rows);
+/* Either the whole tail — feat_2d [rows,257] (2-D-aligned features | visibility mask), feat_3d [rows,256]
+ * (features projected from the reference view), points [rows,3] (world space), feats_in NULL — or, with
+ * feats_in [rows,301] given and the three others NULL, the texture-modulation MLP alone (the reference's
+ * `local_data_batch['feats']` contract).  Outputs alpha, beta [rows,256]; feats_out [rows,301] optional
+ * (whole tail only): the 301-d features the reference materialises. */
+int e3_local_mlp_fwd(const void* packed, const float* feat_2d, const float* feat_3d, const float* points,
+                     const float* feats_in, int64_t rows, float* alpha, float* beta, float* feats_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,15 @@ def make_param(seed, name, shape, variant="default"):
             b = b * 0.1
         return b
 
+    # ---- local branch: SFT fusion MLP and texture-modulation MLP (sft.py:84-109, resnetfc.py:10-62) ----
+    # (the reference zero-initialises the residual / modulation layers; non-zero values exercise every term)
+    if name.startswith("fuse_sft_block.") or ".local_feat_to_tex_modulations_linear." in name:
+        if leaf == "weight":
+            gain = 0.1 if (".local_feat_to_tex_modulations_linear." in name and
+                           (".fc_1." in name or ".shortcut." in name)) else 1.0
+            return _normal(rng, shape, gain * math.sqrt(2.0 / shape[-1]))
+        return _normal(rng, shape, 0.1)
+
     # ---- z -> w mapping (3 x MappingLinear) ------------------------------------
     if name.startswith("style."):
         if leaf == "weight":

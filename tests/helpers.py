@@ -115,3 +115,35 @@ def synthetic_state_dict(size, res, seed, variant="default", local=False):
         sd[name] = torch.from_numpy(
             np.ascontiguousarray(P.make_param(seed, name, shape, variant))).float()
     return sd
+
+
+LOCAL_MLP_SPEC = {
+    "fuse_sft_block.encode_enc.fc_0.weight": (256, 513), "fuse_sft_block.encode_enc.fc_0.bias": (256,),
+    "fuse_sft_block.encode_enc.fc_1.weight": (256, 256), "fuse_sft_block.encode_enc.fc_1.bias": (256,),
+    "fuse_sft_block.encode_enc.shortcut.weight": (256, 513),
+    "fuse_sft_block.scale.0.weight": (256, 256), "fuse_sft_block.scale.0.bias": (256,),
+    "fuse_sft_block.scale.2.weight": (256, 256), "fuse_sft_block.scale.2.bias": (256,),
+    "fuse_sft_block.shift.0.weight": (256, 256), "fuse_sft_block.shift.0.bias": (256,),
+    "fuse_sft_block.shift.2.weight": (256, 256), "fuse_sft_block.shift.2.bias": (256,),
+    "renderer.network.netLocal.local_feat_to_tex_modulations_linear.fc_0.weight": (301, 301),
+    "renderer.network.netLocal.local_feat_to_tex_modulations_linear.fc_0.bias": (301,),
+    "renderer.network.netLocal.local_feat_to_tex_modulations_linear.fc_1.weight": (512, 301),
+    "renderer.network.netLocal.local_feat_to_tex_modulations_linear.fc_1.bias": (512,),
+    "renderer.network.netLocal.local_feat_to_tex_modulations_linear.shortcut.weight": (512, 301),
+}
+
+
+def local_mlp_state_dict(seed, variant="default"):
+    """Synthetic weights of the local branch's per-sample MLPs (Fuse_sft_MLP of the runner, the texture-
+    modulation ResnetBlockFC of netLocal) under the names oracle/gen_golden_local_mlp.py filled them by."""
+    return {k: torch.from_numpy(np.ascontiguousarray(P.make_param(seed, k, shp, variant))).float()
+            for k, shp in LOCAL_MLP_SPEC.items()}
+
+
+def synthetic_local_feats(seed, shape_prefix):
+    """feature_2dAlign | visibility mask [...,257] and feature_3dprojection [...,256] (e3dge_full_runner.py:229-288)."""
+    rng = np.random.Generator(np.random.PCG64([seed, 77]))
+    f2 = rng.standard_normal(tuple(shape_prefix) + (256,)).astype(np.float32)
+    vis = (rng.uniform(size=tuple(shape_prefix) + (1,)) < 0.7).astype(np.float32)
+    f3 = rng.standard_normal(tuple(shape_prefix) + (256,)).astype(np.float32)
+    return torch.from_numpy(np.concatenate([f2, vis], -1)), torch.from_numpy(f3)

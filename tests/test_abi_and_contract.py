@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_lib.exported_symbols()) == set(declared), "ctypes prototypes drifted from the header"
-    assert lib.e3_abi_version() == 3
+    assert lib.e3_abi_version() == 4
     assert lib.e3_siren_packed_bytes() % 128 == 0
 
 

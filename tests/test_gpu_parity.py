@@ -22,7 +22,9 @@ def _build(size, res, seed, variant, n_samples=24, full_pipeline=True, **ropt):
     G = G_pred_latents(model_options(size=size, renderer_spatial_output_dim=res),
                        rendering_options(N_samples=n_samples, **ropt),
                        full_pipeline=full_pipeline).eval()
-    missing = G.load_state_dict(sd, strict=full_pipeline)
+    # the density-only renderer (no_sdf) has no sigmoid_beta parameter (volume_renderer.py:662-663)
+    load = {k: v for k, v in sd.items() if not (ropt.get("no_sdf") and k == "renderer.sigmoid_beta")}
+    missing = G.load_state_dict(load, strict=full_pipeline)
     return G.cuda(), sd
 
 

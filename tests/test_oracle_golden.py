@@ -202,3 +202,37 @@ def test_local_feature_query_oracle_vs_reference_fixture():
             ref = t(k)
             assert (out[k] - ref).abs().max().item() <= 2e-6 * max(ref.abs().max().item(), 1.0), (name, k)
         assert out["in_img"].float().mean().item() > 0.2 and (~out["in_img"]).float().mean().item() > 0.2
+
+
+def test_local_mlp_case():
+    """oracle/local_mlp_oracle.py against the reference's own Fuse_sft_MLP / PosEncoding / ResnetBlockFC and
+    its `--enable_local_model` renderer (tests/golden/local_mlp.npz, oracle/gen_golden_local_mlp.py)."""
+    from oracle import local_mlp_oracle as L
+    from helpers import local_mlp_state_dict, synthetic_local_feats
+    gold, cfg = load_golden("local_mlp")
+    sd = local_mlp_state_dict(41)
+    f2, f3, pts = (torch.from_numpy(gold["mlp." + k]) for k in ("feat_2d", "feat_3d", "points"))
+    with torch.no_grad():
+        feats = L.local_feats(f2, f3, pts, sd)
+        alpha, beta = L.tex_modulation(feats, sd)
+    assert rel_linf(feats, gold["mlp.feats"]) < TOL
+    assert rel_linf(alpha, gold["mlp.alpha"]) < TOL
+    assert rel_linf(beta, gold["mlp.beta"]) < TOL
+    # the whole local renderer pass: global pass -> points -> 301-d features -> modulated render
+    seed = cfg["seed"]
+    gsd = synthetic_state_dict(cfg["size"], cfg["res"], seed, cfg["variant"], local=True)
+    gsd = {k.replace("renderer.network.netGlobal.", "renderer.network."): v for k, v in gsd.items()}
+    lsd = local_mlp_state_dict(seed, cfg["variant"])
+    inp = P.make_inputs(seed, cfg["batch"], 2, cfg["res"])
+    pts = torch.from_numpy(gold["render.points"])
+    f2, f3 = synthetic_local_feats(seed, pts.shape[:-1])
+    with torch.no_grad():
+        mod = L.local_tex_modulation(f2, f3, pts, lsd)
+        out = O.renderer_forward(gsd, inp["cam_poses"], inp["focal"], inp["near"], inp["far"], inp["w"],
+                                 res=cfg["res"], n_samples=cfg["n_samples"], local_mod=mod)
+        glob = O.renderer_forward(gsd, inp["cam_poses"], inp["focal"], inp["near"], inp["far"], inp["w"],
+                                  res=cfg["res"], n_samples=cfg["n_samples"])
+    assert rel_linf(out["points"], gold["render.points"]) < TOL
+    assert rel_linf(glob["features"], gold["render.global_features"]) < TOL
+    for k in ("features", "gen_thumb_imgs", "sdf", "hit_prob", "xyz", "depth"):
+        assert rel_linf(out[k], gold["render." + k]) < 5e-5, k
