@@ -49,7 +49,7 @@ constexpr int LM_KY = 320;     // 301 padded
 constexpr int LM_NR2 = 384;    // 301 padded to whole n-tiles
 constexpr int LM_FEATS = 301, LM_IN2D = 257, LM_PE = 45;
 
-enum { LM_EPI_SPLIT = 0, LM_EPI_RELU = 1, LM_EPI_LRELU = 2, LM_EPI_SFT = 3, LM_EPI_F32 = 4 };
+enum { LM_EPI_SPLIT = 0, LM_EPI_RELU = 1, LM_EPI_LRELU = 2, LM_EPI_SFT = 3, LM_EPI_F32 = 4, LM_EPI_F32_LD = 5 };
 
 struct LinArgs {
   int M, N;        // rows of this chunk; padded output columns (multiple of 128)
@@ -239,8 +239,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_const
 #pragma unroll
             for (int c = 0; c < 16; ++c) f[c] = o[c];
           }
-        } else {  // LM_EPI_F32
-          float* dst = (nb < LM_C ? a.f32_a + nb : a.f32_b + (nb - LM_C)) + (size_t)row * LM_C;
+        } else {  // LM_EPI_F32: [alpha | beta] halves; LM_EPI_F32_LD: one [M, ldo] fp32 matrix
+          float* dst = EPI == LM_EPI_F32_LD
+                           ? a.f32_a + (size_t)row * a.ldo + nb
+                           : (nb < LM_C ? a.f32_a + nb : a.f32_b + (nb - LM_C)) + (size_t)row * LM_C;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4)
             reinterpret_cast<float4*>(dst)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
@@ -391,9 +393,16 @@ struct Operand {  // one activation of the chain in operand form
 };
 
 template <int EPI>
+static int lm_launch_geom(const Operand& a0, const Operand* a1, const StagePtrs& w, StageGeom g, int stage,
+                          int64_t rows, LinArgs args, cudaStream_t stream);
+template <int EPI>
 static int lm_launch(const Operand& a0, const Operand* a1, const StagePtrs& w, int stage, int64_t rows, LinArgs args,
                      cudaStream_t stream) {
-  const StageGeom g = lm_stage(stage);
+  return lm_launch_geom<EPI>(a0, a1, w, lm_stage(stage), stage, rows, args, stream);
+}
+template <int EPI>
+static int lm_launch_geom(const Operand& a0, const Operand* a1, const StagePtrs& w, StageGeom g, int stage,
+                          int64_t rows, LinArgs args, cudaStream_t stream) {
   CUtensorMap mA0h, mA0l, mA1h, mA1l, mBh, mBl;
   int rc;
   if ((rc = lm_make_map(&mA0h, a0.hi, a0.cols, rows, a0.ld))) return rc;
@@ -557,4 +566,70 @@ extern "C" int e3_local_mlp_fwd(const void* packed, const float* feat_2d, const 
     if ((rc = lm_launch<LM_EPI_F32>(Y, &RNET2k, W[5], 5, n, la, stream))) return rc;
   }
   return E3_OK;
+}
+
+
+// ---- generic y = x * W^T (+ bias) on the same kernel: the layer-wise SIREN sweeps of the second-order
+// (eikonal) gradient use it (e3dge_b200/eikonal.py) -----------------------------------------------------
+namespace e3 {
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int64_t n_vec8,
+                                                         __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v0 = reinterpret_cast<const float4*>(x)[2 * i], v1 = reinterpret_cast<const float4*>(x)[2 * i + 1];
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    store_split<8>(hi, lo, (size_t)i * 8, v);
+  }
+}
+}  // namespace e3
+
+extern "C" size_t e3_tc_linear_packed_bytes(int n, int k) {
+  if (n <= 0 || k <= 0) return 0;
+  return (size_t)n * k * 4 + (size_t)n * 4;  // bf16 hi + lo planes [n][k], zero bias [n]
+}
+
+extern "C" int e3_tc_linear_pack(const float* w, int n, int k, void* packed, void* stream_) {
+  E3_REQUIRE(w && packed && n > 0 && k > 0 && n % LM_BN == 0 && k % LM_BK == 0, E3_ERR_BAD_ARG,
+             "e3_tc_linear_pack: needs n %% 128 == 0 and k %% 64 == 0 (got n=%d k=%d)", n, k);
+  cudaStream_t stream = as_stream(stream_);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(packed);
+  __nv_bfloat16* lo = hi + (size_t)n * k;
+  E3_CUDA(cudaMemsetAsync(lo + (size_t)n * k, 0, (size_t)n * 4, stream));
+  lm_place_block_kernel<<<(n * k + 255) / 256, 256, 0, stream>>>(w, n, k, hi, lo, k, 0, 1, 0);
+  E3_CUDA(cudaGetLastError());
+  return E3_OK;
+}
+
+extern "C" size_t e3_tc_linear_workspace_bytes(int64_t rows, int k) {
+  if (rows <= 0 || k <= 0) return 0;
+  return (size_t)((rows + LM_BM - 1) / LM_BM * LM_BM) * k * 4 + 1024;
+}
+
+extern "C" int e3_tc_linear_fwd(const void* packed, int n, int k, const float* x, int64_t rows, const float* bias,
+                                float* y, void* workspace, size_t workspace_bytes, void* stream_) {
+  E3_REQUIRE(packed && x && y && rows >= 0 && n > 0 && k > 0 && n % LM_BN == 0 && k % LM_BK == 0, E3_ERR_BAD_ARG,
+             "e3_tc_linear_fwd: bad argument (needs n %% 128 == 0, k %% 64 == 0)");
+  if (rows == 0) return E3_OK;
+  E3_REQUIRE(rows < ((int64_t)1 << 31) - LM_BM, E3_ERR_BAD_ARG, "e3_tc_linear_fwd: too many rows");
+  E3_REQUIRE(workspace && workspace_bytes >= e3_tc_linear_workspace_bytes(rows, k), E3_ERR_SCRATCH,
+             "e3_tc_linear_fwd: workspace too small");
+  cudaStream_t stream = as_stream(stream_);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  ws += (1024 - (reinterpret_cast<uintptr_t>(ws) & 1023)) & 1023;
+  const int64_t padded = (rows + LM_BM - 1) / LM_BM * LM_BM;
+  Operand X;
+  X.hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  X.lo = X.hi + (size_t)padded * k;
+  X.cols = X.ld = k;
+  const int64_t n_vec8 = rows * k / 8;
+  const int64_t blocks = (n_vec8 + 255) / 256, capb = (int64_t)sm_count() * 16;
+  split_rows_kernel<<<(int)(blocks < capb ? blocks : capb), 256, 0, stream>>>(x, n_vec8, X.hi, X.lo);
+  E3_CUDA(cudaGetLastError());
+  StagePtrs W;
+  W.hi = reinterpret_cast<const __nv_bfloat16*>(packed);
+  W.lo = W.hi + (size_t)n * k;
+  W.bias = bias ? bias : reinterpret_cast<const float*>(W.lo + (size_t)n * k);
+  LinArgs la{};
+  la.f32_a = y;
+  la.ldo = n;
+  return lm_launch_geom<LM_EPI_F32_LD>(X, nullptr, W, StageGeom{n, k}, -1, rows, la, stream);
 }

@@ -124,6 +124,10 @@ _PROTOTYPES = {
     "e3_local_mlp_pack": (c_int, [POINTER(LocalMlpWeights), _fp, _fp]),
     "e3_local_mlp_workspace_bytes": (c_size_t, [c_int64]),
     "e3_local_mlp_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int64, _fp, _fp, _fp, _fp, c_size_t, _fp]),
+    "e3_tc_linear_packed_bytes": (c_size_t, [c_int, c_int]),
+    "e3_tc_linear_pack": (c_int, [_fp, c_int, c_int, _fp, _fp]),
+    "e3_tc_linear_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "e3_tc_linear_fwd": (c_int, [_fp, c_int, c_int, _fp, c_int64, _fp, _fp, _fp, c_size_t, _fp]),
     "e3_pack_inversion_record": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int64, _fp, _fp]),
     "e3_ffma_peak_probe": (c_int, [c_int, _fp, _fp]),
     "e3_ffma_peak_probe_sink_floats": (c_size_t, []),
@@ -193,7 +197,8 @@ KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
                     "e3_styled_conv3x3_fwd_presplit": 1, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
                     "e3_torgb_bwd": 2, "e3_modconv_styles_bwd": 1,
     "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1, "e3_local_feature_query": 1,
-                    "e3_local_mlp_pack": 19, "e3_local_mlp_fwd": 7}
+                    "e3_local_mlp_pack": 19, "e3_local_mlp_fwd": 7,
+                    "e3_tc_linear_pack": 1, "e3_tc_linear_fwd": 2}
 launch_count = 0
 
 # Packed weight images (SIREN stream, conv operands, sum_k W^2) are cached per module and keyed on

@@ -8,8 +8,8 @@ returned dict is ONE CUDA kernel (csrc/render_siren.cu) instead of ~150 ATen lau
 Not provided (SURVEY.md §8 out of scope / "next" rows): marching-cubes mesh extraction
 (`return_mesh`), the 2-D hourglass image filter of the PIFu `netLocal` (an encoder; its per-sample
 half — feature query, SFT fusion, positional encoding, texture-modulation MLP — is local_query.py /
-local_branch.py), second-order gradients (the eikonal terms are returned as values of the backward
-kernel, without a graph of their own).
+local_branch.py).  Second-order gradients: the eikonal terms carry a graph to the latents (eikonal.py);
+nothing else is twice differentiable.
 
 Training (encoders against the frozen generator, trainer.py:881-900, generator frozen at :1569): `_FilmFn`, `_RenderFn`
 and `_PointsFn` bind e3_film_bwd / e3_render_bwd / e3_siren_points_bwd, so gradients reach the
@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .eikonal import eikonal_term
 
 
 class UniformBoxWarp(nn.Module):
@@ -791,14 +792,15 @@ class VolumeFeatureRenderer(nn.Module):
         n = self.out_im_res * self.spatial_ss
         eik = surf_eik = None
         if return_eikonal or kwargs.get("return_surface_eikonal", False):
-            # d sdf / d sample position (volume_renderer.py:855-856): values only, no graph
-            eik = self.sdf_and_gradient(o["points"].reshape(B, -1, 3), styles)[1].reshape(B, n, n, -1, 3)
+            # d sdf / d sample position (volume_renderer.py:796-802, 855-856); with latents that require grad it
+            # carries a graph to them (create_graph=True semantics: eikonal.py)
+            eik = eikonal_term(self, o["points"].detach().reshape(B, -1, 3), styles).reshape(B, n, n, -1, 3)
         if kwargs.get("return_surface_eikonal", False):
             if getattr(self.opt, "use_integrated_surface_normal", False):
                 surf_eik = torch.sum(o["hit_prob"].detach() * eik, 3).unsqueeze(-2)  # :932-934
             else:  # sdf gradient at the integrated surface point (:921-930)
                 xyz_pts = o["xyz"].detach().permute(0, 2, 3, 1).reshape(B, -1, 3)
-                surf_eik = self.sdf_and_gradient(xyz_pts, styles)[1].reshape(B, n, n, 1, 3)
+                surf_eik = eikonal_term(self, xyz_pts, styles).reshape(B, n, n, 1, 3)
         if not return_eikonal:
             eik = None
         out = {
@@ -860,8 +862,8 @@ class VolumeFeatureRenderer(nn.Module):
                 sdf = self.sdf_query(samples.reshape(shp[0], -1, 3), styles)
                 out[f"{k}_rec"] = sdf.reshape(*shp[:-1], 1)
                 if return_surface_eikonal and k == "xyz":  # :1945-1949
-                    out[f"{k}_rec_eikonal_term"] = self.sdf_and_gradient(
-                        samples.reshape(shp[0], -1, 3), styles)[1].reshape(*shp[:-1], 3)
+                    out[f"{k}_rec_eikonal_term"] = eikonal_term(
+                        self, samples.detach().reshape(shp[0], -1, 3), styles).reshape(*shp[:-1], 3)
         if sample_mode:
             out = self._sample_and_collate(out, styles)
             self.sample_mode = False

@@ -458,6 +458,16 @@ int e3_local_mlp_fwd(const void* packed, const float* feat_2d, const float* feat
                      const float* feats_in, int64_t rows, float* alpha, float* beta, float* feats_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Generic fp32-faithful linear layer on the tensor cores (the GEMM kernel of the local MLP tail):
+ * y [rows,n] = x [rows,k] * W^T (+ bias [n]), W [n,k] row-major as nn.Linear stores it; split-bf16 operands
+ * (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM.  n % 128 == 0, k % 64 == 0.  Used by the layer-wise
+ * sweeps of the second-order (eikonal) gradient of the SDF network (volume_renderer.py:796-802). */
+size_t e3_tc_linear_packed_bytes(int n, int k);
+int e3_tc_linear_pack(const float* w, int n, int k, void* packed, void* stream);
+size_t e3_tc_linear_workspace_bytes(int64_t rows, int k);
+int e3_tc_linear_fwd(const void* packed, int n, int k, const float* x, int64_t rows, const float* bias, float* y,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
