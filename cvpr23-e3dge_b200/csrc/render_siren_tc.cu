@@ -547,6 +547,16 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         }
       }
 
+      if (a.in.local_alpha && a.with_view) {
+        // the tile's rows of the local texture modulation (n_valid x 1 KB of alpha and of beta, contiguous)
+        // are requested into L2 now; layer 7's epilogue reads them ~70k cycles later
+        const char* pa = reinterpret_cast<const char*>(a.in.local_alpha + samp0 * SW);
+        const char* pb = reinterpret_cast<const char*>(a.in.local_beta + samp0 * SW);
+        for (int line = ct; line < n_valid * 8; line += TC_COMPUTE) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + (size_t)line * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)line * 128));
+        }
+      }
       if (film_rows_pending) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) (&sm.film[0][0][0])[ct + k * TC_COMPUTE] = pre_film[k];

@@ -217,6 +217,15 @@ def sdf_query(sd, points, styles, dist_radius=0.12):
     return raw[..., 3:4].reshape(points.shape[0], -1, 1)
 
 
+def eikonal_term(sd, points, styles, dist_radius=0.12, create_graph=True):
+    """get_eikonal_term — volume_renderer.py:796-802: d sdf / d point by autograd, with a graph of its own
+    (`create_graph=True`) so that an eikonal loss back-propagates to the latents.  points [B,N,3]."""
+    pts = points.detach().requires_grad_(True)
+    with torch.enable_grad():
+        sdf = sdf_query(sd, pts, styles, dist_radius)
+        return torch.autograd.grad(sdf, pts, grad_outputs=torch.ones_like(sdf), create_graph=create_graph)[0]
+
+
 def query_hitting_probability(sd, wd_space_pts, poses, extrinsics, near, far, styles, n_samples=24,
                               mode="fixed", return_type="weights", static_viewdirs=True,
                               offset_sampling=True, dist_radius=0.12):

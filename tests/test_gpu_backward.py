@@ -360,3 +360,71 @@ def test_local_branch_feats_hook_trains_the_callers_netlocal():
     # sdf does not depend on the texture modulation (volume_renderer.py:206-220)
     assert torch.equal(out["sdf"].detach(), G.renderer(inp["cam_poses"], inp["focal"], inp["near"], inp["far"],
                                                        styles=inp["w"])["sdf"])
+
+
+def test_eikonal_term_is_differentiable_to_the_latents_second_order():
+    """`get_eikonal_term` = autograd.grad(sdf, pts, create_graph=True) (volume_renderer.py:796-802).
+    Stage-1 shapes (N_samples = 18, eikonal_lambda > 0, stage1.sh:46-50): the eikonal loss of trainer.py:618-624
+    on the renderer's `eikonal_term`, differentiated with respect to the w+ latents, against the float64 oracle's
+    double backward; plus the mixed loss (image term + eikonal term) through both backward paths at once."""
+    res, S, B, seed = 8, 18, 2, 97
+    from e3dge_b200 import model_options, rendering_options
+    from e3dge_b200.stylesdf_model import G_pred_latents
+    sd = synthetic_state_dict(64, res, seed, "sharp")
+    G = G_pred_latents(model_options(size=64, renderer_spatial_output_dim=res), rendering_options(N_samples=S),
+                       full_pipeline=False).eval()
+    G.load_state_dict(sd, strict=False)
+    G = G.cuda()
+    for p in G.parameters():
+        p.requires_grad_(False)
+    inp = P.make_inputs(seed, B, 1, res, wplus=True)
+    d = _cuda(inp)
+    w = d["w"].clone().requires_grad_(True)
+    out = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=w, return_eikonal=True)
+    eik = out["eikonal_term"]
+    assert eik.shape == (B, res, res, S, 3) and eik.requires_grad
+    loss_e = ((eik.norm(dim=-1) - 1) ** 2).mean()
+    loss_i = (out["features"] ** 2).mean()
+    g_e, = torch.autograd.grad(loss_e, [w], retain_graph=True)
+    g_mix, = torch.autograd.grad(loss_i + 0.1 * loss_e, [w])
+    # float64 oracle
+    sd64 = O.cast_state_dict(sd, torch.float64)
+    w64 = inp["w"].double().requires_grad_(True)
+    r64 = O.renderer_forward(sd64, inp["cam_poses"].double(), inp["focal"].double(), inp["near"].double(),
+                             inp["far"].double(), w64, res=res, n_samples=S)
+    e64 = O.eikonal_term(sd64, r64["points"].detach().reshape(B, -1, 3), w64).reshape(B, res, res, S, 3)
+    l64 = ((e64.norm(dim=-1) - 1) ** 2).mean()
+    ge64, = torch.autograd.grad(l64, [w64], retain_graph=True)
+    gm64, = torch.autograd.grad((r64["features"] ** 2).mean() + 0.1 * l64, [w64])
+    assert rel_linf(eik.detach().cpu(), e64.detach()) < TOL
+    assert ge64.abs().max() > 0
+    assert rel_linf(g_e.cpu(), ge64) < TOL, rel_linf(g_e.cpu(), ge64)
+    assert rel_linf(g_mix.cpu(), gm64) < TOL, rel_linf(g_mix.cpu(), gm64)
+    # no graph is built when nothing asks for one
+    with torch.no_grad():
+        plain = G.renderer(d["cam_poses"], d["focal"], d["near"], d["far"], styles=d["w"], return_eikonal=True)
+    assert not plain["eikonal_term"].requires_grad
+    assert torch.equal(plain["eikonal_term"], eik.detach())
+
+
+def test_tc_linear_matches_fp32_matmul():
+    """e3_tc_linear_fwd (the generic tcgen05 GEMM behind the local MLP tail and the eikonal sweeps): split-bf16
+    products against a float64 matmul, ragged row counts, with and without bias."""
+    from e3dge_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    for rows, n, k in ((1, 128, 64), (300, 256, 256), (1027, 384, 320)):
+        x = torch.randn(rows, k, generator=g)
+        w = torch.randn(n, k, generator=g) / k ** 0.5
+        b = torch.randn(n, generator=g)
+        xc, wc, bc = x.cuda(), w.cuda(), b.cuda()
+        packed = torch.empty(lib.e3_tc_linear_packed_bytes(n, k) // 4, device="cuda")
+        _lib.check(lib.e3_tc_linear_pack(_lib.ptr(wc), n, k, _lib.ptr(packed), _lib.cur_stream()), "e3_tc_linear_pack")
+        nbytes = lib.e3_tc_linear_workspace_bytes(rows, k)
+        ws = torch.empty(nbytes // 4 + 1, device="cuda")
+        for bias in (None, bc):
+            y = torch.empty(rows, n, device="cuda")
+            _lib.check(lib.e3_tc_linear_fwd(_lib.ptr(packed), n, k, _lib.ptr(xc), rows, _lib.ptr(bias), _lib.ptr(y),
+                                            _lib.ptr(ws), nbytes, _lib.cur_stream()), "e3_tc_linear_fwd")
+            ref = x.double() @ w.double().t() + (b.double() if bias is not None else 0)
+            assert rel_linf(y.cpu(), ref) < 2e-5, (rows, n, k)

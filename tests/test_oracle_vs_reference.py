@@ -78,3 +78,35 @@ print("RESULT" + json.dumps(res))
         assert case["in_img"]
         for k in ("proj_xy", "depth", "feats"):
             assert case[k] < 2e-6, (k, case[k])
+
+
+def test_second_order_eikonal_gradient_of_the_oracle_matches_the_live_reference():
+    """The reference's own `get_eikonal_term` (autograd.grad(..., create_graph=True), volume_renderer.py:796-802)
+    inside its renderer, an eikonal loss on it (losses/gan_loss.py) and its gradient with respect to the w+
+    latents — against oracle.eikonal_term differentiated the same way."""
+    script = r"""
+import json, sys, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/tests')
+from oracle import ref_harness as rh, params as P, stylesdf_oracle as O
+from helpers import rel_linf
+ref = rh.load_reference()
+torch.manual_seed(4)
+G = ref.stylesdf_model.G_pred_latents(rh.model_opt(size=64, renderer_spatial_output_dim=8),
+                                      rh.rendering_opt(N_samples=6), full_pipeline=False).eval()
+sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+inp = P.make_inputs(6, 2, 2, 8)
+w = inp['w'].clone().requires_grad_(True)
+out = G.renderer(inp['cam_poses'], inp['focal'], inp['near'], inp['far'], styles=w, return_eikonal=True)
+eik = out['eikonal_term']
+loss = ((eik.norm(dim=-1) - 1) ** 2).mean()
+g_ref, = torch.autograd.grad(loss, [w])
+w2 = inp['w'].clone().requires_grad_(True)
+e2 = O.eikonal_term(sd, out['points'].detach().reshape(2, -1, 3), w2).reshape(eik.shape)
+g_or, = torch.autograd.grad(((e2.norm(dim=-1) - 1) ** 2).mean(), [w2])
+print('RESULT' + json.dumps({'eik': rel_linf(e2.detach(), eik.detach()), 'grad': rel_linf(g_or, g_ref),
+                             'gmax': float(g_ref.abs().max())}))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.split("RESULT")[-1])
+    assert res["gmax"] > 0 and res["eik"] < 2e-5 and res["grad"] < 1e-4, res
