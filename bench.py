@@ -136,9 +136,14 @@ def make_inputs(rank):
 
 
 def run_ours(args):
+    global BATCH
     import torch.distributed as dist
     from e3dge_b200 import _lib, parallel as par
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong":  # fixed total work: the global batch is split into contiguous shards
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        BATCH = args.global_batch // world
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
@@ -296,9 +301,11 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic (random latents/cameras, random-init weights)",
-            "config": {"workload": WORKLOAD, "size": SIZE, "render_res": RES,
+            "config": {"workload": WORKLOAD if args.scaling == "weak" else WORKLOAD.replace(
+                           "batch=8 per GPU", f"global batch {BATCH * world} split over {world} GPU(s)"),
+                       "size": SIZE, "render_res": RES,
                        "n_samples": N_SAMPLES, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "parallelism": f"image-parallel dp{world}, 1 all-gather of latents/metrics per step",
                        "l2": "256 MiB memset between timed steps, outside the per-step CUDA-event pairs",
@@ -607,6 +614,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: 8 frames per GPU (default, the driver's scaling run); strong: --global-batch frames "
+                         "in total, split over the ranks (BASELINE.json configs[2]: 32 over 8 GPUs)")
+    ap.add_argument("--global-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact-fp32", action="store_true", help="skip the exact-fp32 back-end timing")
     ap.add_argument("--no-local-branch", action="store_true", help="skip the local-branch frame timing")

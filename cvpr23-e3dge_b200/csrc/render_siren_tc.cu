@@ -656,10 +656,13 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               dst[0] = make_float4(v[0], v[1], v[2], v[3]);
               dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
-            if (la) {
+            if (la) {  // two 16-byte loads per operand (n0 is a multiple of 8, rows are 1 KB apart)
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(la + n0)), a1 = __ldg(reinterpret_cast<const float4*>(la + n0) + 1);
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(lb + n0)), b1 = __ldg(reinterpret_cast<const float4*>(lb + n0) + 1);
+              const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[i] = __fadd_rn(__fmul_rn(__fadd_rn(la[n0 + i], 1.f), v[i]), lb[n0 + i]);
+              for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(__fmul_rn(__fadd_rn(al[i], 1.f), v[i]), be[i]);
             }
           }
           if (taps && (l & 1) == 0) store_tap(l >> 1, n0, v);
