@@ -46,6 +46,7 @@ namespace e3 {
 
 constexpr int TCM = 128;                 // rows per tile
 constexpr int TC_RING = 4;               // weight stages
+constexpr int NS_RING = 8;               // N-split pairs: the same 64 KB as 8 stages of 64 rows
 constexpr int TC_COMPUTE_WARPS = 16;
 constexpr int TC_COMPUTE = TC_COMPUTE_WARPS * 32;
 constexpr int TC_NTHREADS = 64 + TC_COMPUTE;  // producer warp + MMA warp + compute warps
@@ -66,8 +67,9 @@ struct SmemTC {
   float sdf_part[4][TCM];   // partial head sums of the 4 column quarters
   float rgb_part[4][3][TCM];
   float ray_o[3][TCM], ray_d[3][TCM];
-  uint64_t full[TC_RING], empty[TC_RING];
+  uint64_t full[NS_RING], empty[NS_RING];  // TC_RING stages of 16 KB, or NS_RING of 8 KB (N-split pairs)
   uint64_t a_ready[4], d_ready;
+  uint64_t d_ready1;  // N-split pairs: accumulator columns of the second N-half (channel blocks 1, 3) are complete
   uint64_t a_half;  // EPI bit 1: channels [0,32) of block 0 are published (the next layer's first MMAs start)
   uint64_t a_tail;  // pairs: channels [192,224) of block 3 are published (half of the last k-block's MMAs start)
   uint32_t tmem_slot;
@@ -180,9 +182,15 @@ template <int MODE, int CL, bool STASH, int EPI>
 // 18 warps: one scheduler holds 5 of them, so 16384 / (5 * 32) = 102 -> 96 registers per thread
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_constant__ CUtensorMap wmap,
-                       const int use_wmap) {
-  static_assert(EPI == 0 || EPI == 1 || EPI == 3 || EPI == 7, "the half-block column mapping needs the packed epilogue");
+                       const __grid_constant__ CUtensorMap wmap64, const int use_wmap) {
+  static_assert(EPI == 0 || EPI == 1 || EPI == 3 || EPI == 7 || EPI == 15, "the half-block column mapping needs the packed epilogue");
   constexpr bool PAIR = (EPI & 4) != 0;
+  // N-split pairs (EPI bit 3): every 256-column layer is issued as two 128-column halves, interleaved by k-block
+  // (units (n0,k0) (n0,k2) (n1,k0) (n1,k2) (n0,k1) (n0,k3) (n1,k1) (n1,k3)), so that the first half — channel
+  // blocks 0 and 2 — is complete, and its epilogue running, while the tensor pipe still works on the second
+  // one: the per-layer bubble (drain + first block of the epilogue) shrinks from ~2.5k to ~1.3k cycles.
+  constexpr bool NS = (EPI & 8) != 0;
+  static_assert(!NS || PAIR, "the N-split is built on the CTA-pair MMA stream");
   static_assert(!PAIR || CL == 2, "CTA pairs are clusters of two");
   const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = pair_rank == 0;
@@ -192,7 +200,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_RING; ++s) {
+    for (int s = 0; s < NS_RING; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], PAIR ? 1 : CL);
     }
@@ -201,6 +209,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 #pragma unroll
     for (int j = 0; j < 4; ++j) mbar_init(&sm.a_ready[j], n_arrive);
     mbar_init(&sm.d_ready, 1);
+    mbar_init(&sm.d_ready1, 1);
     mbar_init(&sm.a_half, n_arrive);
     mbar_init(&sm.a_tail, n_arrive);
     fence_mbar_init();
@@ -231,7 +240,27 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       const int per_tile = gemm_layers * TC_TILES_PER_LAYER;
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
-        if (PAIR) {
+        if (NS) {
+          // one stage = 64 of this CTA's 128 rows of a weight block (8 KB), in the order the MMA units consume
+          // them: (nh, kb) = (0,0) (0,2) (1,0) (1,2) (0,1) (0,3) (1,1) (1,3), W_hi then W_lo each
+          for (int l = 0; l < gemm_layers; ++l) {
+#pragma unroll 1
+            for (int u = 0; u < 8; ++u) {
+              const int nh = (u >> 1) & 1, kb = (u & 1) * 2 + (u >> 2);
+#pragma unroll 1
+              for (int p = 0; p < 2; ++p) {
+                mbar_wait(&sm.empty[stage], phase ^ 1);
+                if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * (TC_TILE_BYTES / 2));
+                tc::tma_load_2d_pair(sm.ring + stage * (TC_TILE_BYTES / 2), &wmap64, tc::map_to_cta(&sm.full[stage], 0), 0,
+                                     (2 * (l * 8 + kb * 2 + p) + (int)pair_rank) * 128 + nh * 64);
+                if (++stage == NS_RING) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        } else if (PAIR) {
           // one stage = one 256(n) x 64(k) block over the pair: this CTA fetches its n-half, the bytes of
           // both halves are counted on the leader's barrier
           for (int c = 0; c < per_tile / 2; ++c) {
@@ -268,7 +297,59 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (PAIR && leader && lane == 0) {
+    if (NS && leader && lane == 0) {
+      // ===== CTA pair, N-split: units of 12 MMAs 256 x 128 x 16 =====
+      const uint32_t idesc = tc::make_idesc_bf16_f32(256, 128);
+      const uint32_t a_hi0 = smem_u32(sm.a_hi), a_lo0 = smem_u32(sm.a_lo);
+      uint32_t stage = 0, phase = 0, pa = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        for (int l = 0; l < gemm_layers; ++l) {
+#pragma unroll 1
+          for (int u = 0; u < 8; ++u) {
+            const int nh = (u >> 1) & 1, kb = (u & 1) * 2 + (u >> 2);
+            const uint32_t dcol = tmem_base + (uint32_t)(l & 1) * 256 + (uint32_t)nh * 128;
+            const bool first = u == 0;  // block 0 arrives in two halves (a_half, then a_ready[0])
+            mbar_wait(first ? &sm.a_half : &sm.a_ready[kb], pa);
+            tc::fence_after_thread_sync();
+            const uint64_t dAh = tc::make_smem_desc_sw128(a_hi0 + kb * A_KBLOCK_BYTES);
+            const uint64_t dAl = tc::make_smem_desc_sw128(a_lo0 + kb * A_KBLOCK_BYTES);
+            const uint32_t s1 = (stage + 1 == NS_RING) ? 0 : stage + 1;  // W_lo piece (ring of 8: same phase)
+            const uint64_t dB0 = tc::make_smem_desc_sw128(smem_u32(sm.ring + stage * (TC_TILE_BYTES / 2)));
+            const uint64_t dB1 = tc::make_smem_desc_sw128(smem_u32(sm.ring + s1 * (TC_TILE_BYTES / 2)));
+            auto hi_block = [&](int ks) {  // h_hi * W_hi + h_lo * W_hi
+              const uint64_t bk = tc::advance_desc_k(dB0, ks);
+              tc::mma_bf16_ss_pair(dcol, tc::advance_desc_k(dAh, ks), bk, idesc, (kb | ks) != 0);
+              tc::mma_bf16_ss_pair(dcol, tc::advance_desc_k(dAl, ks), bk, idesc, true);
+            };
+            auto lo_block = [&](int ks) {  // h_hi * W_lo
+              tc::mma_bf16_ss_pair(dcol, tc::advance_desc_k(dAh, ks), tc::advance_desc_k(dB1, ks), idesc, true);
+            };
+            mbar_wait(&sm.full[stage], phase);
+            tc::fence_after_thread_sync();
+            hi_block(0), hi_block(1);
+            if (first) {
+              mbar_wait(&sm.a_ready[0], pa);  // second half of block 0
+              tc::fence_after_thread_sync();
+            }
+            hi_block(2), hi_block(3);
+            tc::mma_commit_pair(&sm.empty[stage], 3);
+            mbar_wait(&sm.full[s1], phase);  // stage is even here: its successor never wraps
+            tc::fence_after_thread_sync();
+            lo_block(0), lo_block(1), lo_block(2), lo_block(3);
+            tc::mma_commit_pair(&sm.empty[s1], 3);
+            stage += 2;
+            if (stage == NS_RING) {
+              stage = 0;
+              phase ^= 1;
+            }
+            if (u == 5) tc::mma_commit_pair(&sm.d_ready, 3);   // half 0 (channel blocks 0, 2) complete
+            if (u == 7) tc::mma_commit_pair(&sm.d_ready1, 3);  // half 1 (channel blocks 1, 3) complete
+          }
+          pa ^= 1;
+        }
+      }
+    }
+    if (PAIR && !NS && leader && lane == 0) {
       // ===== CTA pair: one tcgen05.mma cta_group::2 stream over both CTAs' tiles (M = 256) =====
       // A k-block's 12 MMAs use two ring stages (W_hi block, W_lo block).  Blocks 0 and 3 arrive in two
       // halves (a_half / a_tail, then a_ready): the k-steps of the first half are issued for both weight
@@ -628,8 +709,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
 
       // ---- hidden layers 1..7: TMEM -> FiLM + sin -> next A operand, 64 channels at a time ----
       float sdf_acc = 0.f;
+      // accumulator column of channel block j: N-split pairs lay a layer out as [block 0 | block 2 | block 1 | block 3]
+      // (each 128-column MMA takes 64 weight rows from either CTA of the pair)
+      auto dcb = [](int j) -> uint32_t { return NS ? (uint32_t)((j & 1) * 128 + (j >> 1) * 64) : (uint32_t)(j * 64); };
       for (int l = 1; l < 8; ++l) {
         mbar_wait(&sm.d_ready, pd);
+        const uint32_t pd_l = pd;
         pd ^= 1;
         if (tr) a.trace[l * 8] = clock64();
         tc::fence_after_thread_sync();
@@ -691,7 +776,12 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
           finish_group(j, g8, n0, v);
         };
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = NS ? ((jj & 1) * 2 + (jj >> 1)) : jj;  // N-split: blocks 0, 2 (first half), then 1, 3
+          if (NS && jj == 2) {
+            mbar_wait(&sm.d_ready1, pd_l);
+            tc::fence_after_thread_sync();
+          }
           if (EPI & 1) {
             uint32_t accr[16];
             float4 fg[4], fb[4];
@@ -704,10 +794,10 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
               // TMEM reads run at ~64 B/clk per SM: sixteen warps asking for 16 columns each wait ~500
               // cycles.  The 8 columns of the first half-block are requested alone, the other 8 land under
               // their processing.
-              tc::tmem_ld_32x8_issue(dsrc0 + j * 64 + hw * 8, accr);
+              tc::tmem_ld_32x8_issue(dsrc0 + dcb(j) + hw * 8, accr);
               film_rows(0), film_rows(1);
               tc::tmem_ld_wait8(accr);
-              tc::tmem_ld_32x8_issue(dsrc0 + j * 64 + 32 + hw * 8, accr + 8);
+              tc::tmem_ld_32x8_issue(dsrc0 + dcb(j) + 32 + hw * 8, accr + 8);
               film_rows(2), film_rows(3);
               if (tr && l == 3) a.trace[384 + j * 8] = clock64();
               packed_group(j, 0, accr, fg, fb);
@@ -816,6 +906,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
       if (a.with_view) {
         // ---- view layer epilogue: + W_dir*viewdir, FiLM, sin; rgb head; weighted feature sum ----
         mbar_wait(&sm.d_ready, pd);
+        if (NS) mbar_wait(&sm.d_ready1, pd);
         pd ^= 1;
         if (tr) a.trace[64] = clock64();
         tc::fence_after_thread_sync();
@@ -827,7 +918,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
         // the TMEM read of block j+1 is in flight while block j is processed (this epilogue is on the
         // tile's critical path: nothing else runs on the SM)
         uint32_t nxt[16];
-        if (EPI & 1) tc::tmem_ld_32x16_issue(dsrc, nxt);
+        if (EPI & 1) tc::tmem_ld_32x16_issue(dsrc + dcb(0), nxt);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           float acc[16];
@@ -835,7 +926,7 @@ siren_render_tc_kernel(const __grid_constant__ RenderArgs a, const __grid_consta
             tc::tmem_ld_wait16(nxt);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(nxt[i]);
-            if (j < 3) tc::tmem_ld_32x16_issue(dsrc + (j + 1) * 64, nxt);
+            if (j < 3) tc::tmem_ld_32x16_issue(dsrc + dcb(j + 1), nxt);
           } else {
             tc::tmem_ld_32x16(dsrc + j * 64, acc);
           }
@@ -1028,12 +1119,16 @@ static int launch_tc_variant(const RenderArgs& a, cudaStream_t stream) {
   const uint32_t wbox[2] = {64, 128};
   int rc = make_tensor_map_bf16(&wmap, a.packed + OFF_TC_STREAM, 2, wdims, wstr, wbox, /*swizzle128=*/false);
   if (rc) return rc;
+  CUtensorMap wmap64;  // N-split pairs: 64-row pieces of the same stream
+  const uint32_t wbox64[2] = {64, 64};
+  rc = make_tensor_map_bf16(&wmap64, a.packed + OFF_TC_STREAM, 2, wdims, wstr, wbox64, /*swizzle128=*/false);
+  if (rc) return rc;
   static int use_wmap = -1;
   if (use_wmap < 0) {
     const char* e = getenv("E3DGE_RENDER_WSTREAM");  // measurement aid: "bulk" | "tensor"
     use_wmap = (e && e[0] == 'b') ? 0 : 1;
   }
-  E3_CUDA(cudaLaunchKernelEx(&cfg, fn, a, wmap, use_wmap));
+  E3_CUDA(cudaLaunchKernelEx(&cfg, fn, a, wmap, wmap64, use_wmap));
   return E3_OK;
 }
 
@@ -1059,12 +1154,12 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   const int cl = render_cluster_size();
   static int epi = -1;
   if (epi < 0) {
-    // epilogue / MMA-issue variant (template parameter EPI): 7 = CTA pairs (default), 3 = one CTA per
-    // MMA stream, 0 = the scalar epilogue the what-if flags and the multicast weight-stream clusters
+    // epilogue / MMA-issue variant (template parameter EPI): 15 = CTA pairs with N-split layers (default),
+    // 7 = CTA pairs, whole 256-column layers, 3 = one CTA per MMA stream, 0 = the scalar epilogue the what-if flags and the multicast weight-stream clusters
     // (E3DGE_RENDER_CLUSTER) apply to
     const char* e = getenv("E3DGE_RENDER_EPI");
-    epi = e ? atoi(e) : 7;
-    if (epi != 0 && epi != 3) epi = 7;
+    epi = e ? atoi(e) : 15;
+    if (epi != 0 && epi != 3 && epi != 7) epi = 15;
   }
   // every variant computes each value with the same operations, but the order of the accumulations (MMA
   // issue order, head sums per thread-to-column mapping) differs: the training forward (stash) is the
@@ -1072,8 +1167,10 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   if (a.stash) {
     if (epi == 0) return mode == 0 ? launch_tc_variant<0, 1, true, 0>(a, stream) : launch_tc_variant<1, 1, true, 0>(a, stream);
     if (epi == 3) return mode == 0 ? launch_tc_variant<0, 1, true, 3>(a, stream) : launch_tc_variant<1, 1, true, 3>(a, stream);
-    return mode == 0 ? launch_tc_variant<0, 2, true, 7>(a, stream) : launch_tc_variant<1, 2, true, 7>(a, stream);
+    if (epi == 7) return mode == 0 ? launch_tc_variant<0, 2, true, 7>(a, stream) : launch_tc_variant<1, 2, true, 7>(a, stream);
+    return mode == 0 ? launch_tc_variant<0, 2, true, 15>(a, stream) : launch_tc_variant<1, 2, true, 15>(a, stream);
   }
+  if (epi == 15) return mode == 0 ? launch_tc_variant<0, 2, false, 15>(a, stream) : launch_tc_variant<1, 2, false, 15>(a, stream);
   if (epi == 7) return mode == 0 ? launch_tc_variant<0, 2, false, 7>(a, stream) : launch_tc_variant<1, 2, false, 7>(a, stream);
   if (epi == 3) return mode == 0 ? launch_tc_variant<0, 1, false, 3>(a, stream) : launch_tc_variant<1, 1, false, 3>(a, stream);
   if (mode == 0) {
