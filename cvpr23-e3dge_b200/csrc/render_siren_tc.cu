@@ -1154,12 +1154,14 @@ int launch_render_tc(const RenderArgs& a_in, int mode, cudaStream_t stream) {
   const int cl = render_cluster_size();
   static int epi = -1;
   if (epi < 0) {
-    // epilogue / MMA-issue variant (template parameter EPI): 15 = CTA pairs with N-split layers (default),
-    // 7 = CTA pairs, whole 256-column layers, 3 = one CTA per MMA stream, 0 = the scalar epilogue the what-if flags and the multicast weight-stream clusters
+    // epilogue / MMA-issue variant (template parameter EPI): 7 = CTA pairs, whole 256-column layers (default),
+    // 15 = CTA pairs with N-split layers (measured slower: 2.83 vs 2.37 ms, profiles/r02_ab_render_nsplit.txt —
+    // the 128-column MMAs re-read the A operand twice as often and the shared-memory pipe paces them),
+    // 3 = one CTA per MMA stream, 0 = the scalar epilogue the what-if flags and the multicast weight-stream clusters
     // (E3DGE_RENDER_CLUSTER) apply to
     const char* e = getenv("E3DGE_RENDER_EPI");
-    epi = e ? atoi(e) : 15;
-    if (epi != 0 && epi != 3 && epi != 7) epi = 15;
+    epi = e ? atoi(e) : 7;
+    if (epi != 0 && epi != 3 && epi != 15) epi = 7;
   }
   // every variant computes each value with the same operations, but the order of the accumulations (MMA
   // issue order, head sums per thread-to-column mapping) differs: the training forward (stash) is the
