@@ -322,6 +322,11 @@ def run_ours(args):
     if rank == 0:
         line.update(kernel_roofline(G, resident, dev, flush, args))
         line["train_step"] = train_step_timing(G, resident, flush, args)
+        if world == 1 and not args.no_full_frame:
+            try:
+                line["full_frame"] = full_frame_timing(G, dev, flush, args, world, sync_all)
+            except Exception as exc:
+                line["full_frame"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and not args.no_local_branch:
             try:
                 line["local_branch"] = local_branch_timing(G, sd, resident, dev, flush, args)
@@ -490,6 +495,63 @@ def local_branch_timing(G, sd, inp, dev, flush, args):
                          "peak_source": how + " (cuBLAS bf16 burst)"}}
 
 
+def full_frame_timing(G, dev, flush, args, world, sync_all):
+    """Secondary figure: the WHOLE inversion frame of BASELINE.json's metric — image -> IR-SE50/FPN encoder (+ mean
+    latents) and CoordConv pose net -> cameras -> renderer -> decoder (AERunner.image2image, trainer.py:773-840).
+    The two front-end conv nets are cuDNN through PyTorch (bf16 autocast, channels-last), recorded into the same
+    CUDA graph as the generator; `e2e` copies the batch of images in from pinned host memory and the result out."""
+    import numpy as np
+    import synthetic_inputs as P
+    from e3dge_b200 import model_options
+    from e3dge_b200.frontend import HybridGradualStyleEncoder_V2, InversionPipeline, VolumeRenderDiscriminator
+    from e3dge_b200.graphed import GraphedCall
+    enc = P.fill_module(HybridGradualStyleEncoder_V2(50, "ir_se", -1).eval(), "encoder.", SEED)
+    pose = P.fill_module(VolumeRenderDiscriminator(model_options(renderer_spatial_output_dim=RES)).eval(),
+                         "volume_discriminator.", SEED)
+    pipe = InversionPipeline(G, enc, pose, amp=True).to(dev).eval()
+    g = np.random.Generator(np.random.PCG64(SEED))
+    img_in = torch.from_numpy(g.uniform(-1, 1, (BATCH, 3, SIZE, SIZE)).astype(np.float32)).pin_memory()
+    static = img_in.to(dev)
+    img_out = torch.empty(BATCH, 3, SIZE, SIZE).pin_memory()
+
+    def core():
+        with torch.no_grad():
+            return pipe(static, randomize_noise=True, return_xyz=True, return_sdf=True)
+
+    def front_only():
+        with torch.no_grad():
+            thumb = torch.nn.functional.adaptive_avg_pool2d(static, (64, 64))
+            return pipe.image2latents(static), pipe.image2camsettings(thumb)
+    gcall, gfront = GraphedCall(core), GraphedCall(front_only)
+
+    def e2e():
+        static.copy_(img_in, non_blocking=True)
+        out = gcall()
+        img_out.copy_(out["gen_imgs"], non_blocking=True)
+
+    def med(fn, n):
+        for _ in range(3):
+            fn()
+        sync_all()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+    n = max(3, min(args.steps, 10))
+    ms, ms_e2e, ms_front = med(gcall, n), med(e2e, n), med(gfront, n)
+    return {"what": "whole inversion frame: encoder (IR-SE50 + FPN, bf16 channels-last cuDNN) + pose net + cameras + "
+                    "renderer + decoder in one CUDA graph, batch %d per GPU" % BATCH,
+            "ms_per_step": ms, "value": BATCH * world / (ms / 1e3), "e2e": BATCH * world / (ms_e2e / 1e3),
+            "unit": "frames/s", "front_end_ms": ms_front, "h2d_bytes_per_step": img_in.numel() * 4,
+            "d2h_bytes_per_step": img_out.numel() * 4}
+
+
 def train_step_timing(G, inp, flush, args):
     """Secondary figure (not the headline metric): the same batch through the generator with the
     backward kernels — forward writing the stash, then dL/d(w+), dL/d(decoder latent) of an image
@@ -621,6 +683,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact-fp32", action="store_true", help="skip the exact-fp32 back-end timing")
     ap.add_argument("--no-local-branch", action="store_true", help="skip the local-branch frame timing")
+    ap.add_argument("--no-full-frame", action="store_true", help="skip the encoder -> render -> decode frame timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -83,6 +83,22 @@ def make_param(seed, name, shape, variant="default"):
             return _normal(rng, shape, gain * math.sqrt(2.0 / shape[-1]))
         return _normal(rng, shape, 0.1)
 
+    # ---- front end: IR-SE50 / FPN encoder and the CoordConv pose net (conv nets with BatchNorm / PReLU) ----
+    if name.startswith("encoder.") or name.startswith("volume_discriminator."):
+        if leaf == "num_batches_tracked":
+            return np.zeros(shape)
+        if leaf == "running_mean":
+            return _normal(rng, shape, 0.05)
+        if leaf == "running_var":
+            return 1.0 + np.abs(_normal(rng, shape, 0.1))
+        if len(shape) >= 2:  # conv / linear weights: variance-preserving through the ~50-layer trunk
+            fan_in = int(np.prod(shape[1:]))
+            return _normal(rng, shape, math.sqrt(1.0 / fan_in))
+        if leaf == "weight":  # BatchNorm scale / PReLU slope (1-d)
+            return (0.25 + _normal(rng, shape, 0.02)) if ".res_layer.2." in name or name.endswith("input_layer.2.weight") \
+                else 1.0 + _normal(rng, shape, 0.05)
+        return _normal(rng, shape, 0.05)
+
     # ---- z -> w mapping (3 x MappingLinear) ------------------------------------
     if name.startswith("style."):
         if leaf == "weight":
@@ -124,6 +140,14 @@ def fill_state_dict(state_dict, seed=0, variant="default"):
         v = make_param(seed, name, ref.shape, variant)
         out[name] = torch.from_numpy(np.ascontiguousarray(v)).to(torch.float32)
     return out
+
+
+def fill_module(module, prefix, seed=0, variant="default"):
+    """Loads make_param's values into every entry of `module.state_dict()` (names prefixed by `prefix`)."""
+    sd = {k: torch.from_numpy(np.ascontiguousarray(make_param(seed, prefix + k, v.shape, variant))).to(v.dtype)
+          for k, v in module.state_dict().items()}
+    module.load_state_dict(sd, strict=True)
+    return module
 
 
 def make_inputs(seed, batch, n_dec_latent, res, fov_deg=6.0, dist_radius=0.12,
