@@ -37,7 +37,12 @@ namespace e3 {
 constexpr int LM_BM = 128, LM_BN = 128, LM_BK = 64, LM_STAGES = 3;
 constexpr int LM_TILE_BYTES = 128 * 128;           // one operand tile: 128 rows x 64 bf16
 constexpr int LM_STAGE_BYTES = 4 * LM_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
-constexpr int LM_SMEM_BYTES = LM_STAGES * LM_STAGE_BYTES + 256 + 1024;
+// Epilogue staging (split / fp32 outputs): each group of 4 epilogue warps (one per TMEM lane quarter) owns a
+// 128-row x 128-byte buffer in the TMA 128B-swizzled layout and hands it to a TMA tensor store — full-line
+// writes instead of 32 lanes x 16 B to 32 different rows per instruction (which held the epilogue of the short-K
+// stages at 3x their MMA time, profiles/r02_tc_linear_kernel.txt).
+constexpr int LM_OUT_BYTES = LM_BM * 128;
+constexpr int LM_SMEM_BYTES = LM_STAGES * LM_STAGE_BYTES + 2 * LM_OUT_BYTES + 256 + 1024;
 constexpr int LM_EPI_WARPS = 8;
 constexpr int LM_THREADS = 64 + LM_EPI_WARPS * 32;
 
@@ -81,10 +86,12 @@ __global__ void __launch_bounds__(LM_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
                  const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmO_a, const __grid_constant__ CUtensorMap tmO_b,
                  const __grid_constant__ LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + LM_STAGES * LM_STAGE_BYTES);
+  uint8_t* out_stage = smem + LM_STAGES * LM_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + 2 * LM_OUT_BYTES);
   uint64_t* empty = full + LM_STAGES;
   uint64_t* acc_full = empty + LM_STAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -102,6 +109,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_const
     tc::prefetch_tensormap(&tmA1_lo);
     tc::prefetch_tensormap(&tmB_hi);
     tc::prefetch_tensormap(&tmB_lo);
+    if (EPI != LM_EPI_SFT) {
+      tc::prefetch_tensormap(&tmO_a);
+      tc::prefetch_tensormap(&tmO_b);
+    }
 #pragma unroll
     for (int s = 0; s < LM_STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -184,6 +195,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_const
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;  // which two of the tile's four 32-column chunks
     const int m = q * 32 + lane;
+    uint8_t* obuf = out_stage + chalf * LM_OUT_BYTES;
+    const bool store_leader = q == 0 && lane == 0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_tiles_n) * LM_BM, n0 = (tile % n_tiles_n) * LM_BN;
@@ -192,17 +205,18 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_const
       const bool valid = row < a.M;
       mbar_wait(&acc_full[buf], use & 1);
       tc::fence_after_thread_sync();
-#pragma unroll 1
-      for (int chunk = chalf * 2; chunk < chalf * 2 + 2; ++chunk) {
+      uint32_t hw[2][16], lw[2][16];  // split modes: this thread's 64 outputs as bf16 hi / lo pairs
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int chunk = chalf * 2 + cc;
         float v[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * LM_BN + chunk * 32, v);
-        if (chunk == chalf * 2 + 1) {  // this warp's share is read: tell the MMA warp
+        if (cc == 1) {  // this warp's share is read: tell the MMA warp
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         const int nb = n0 + chunk * 32;
-        if (!valid) continue;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b4 = *reinterpret_cast<const float4*>(a.bias + nb + j4 * 4);
@@ -216,8 +230,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_const
           for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
         }
         if (EPI == LM_EPI_SPLIT || EPI == LM_EPI_RELU || EPI == LM_EPI_LRELU) {
-          store_split<32>(a.out_hi, a.out_lo, (size_t)row * a.ldo + nb, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split_pair_bf16(v[2 * i], v[2 * i + 1], hw[cc][i], lw[cc][i]);
         } else if (EPI == LM_EPI_SFT) {
+          if (!valid) continue;
           const int c0 = nb >> 1;  // 16 (scale, shift) pairs -> channels [c0, c0 + 16)
           float o[16], ro[16];
 #pragma unroll
@@ -239,16 +255,41 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_const
 #pragma unroll
             for (int c = 0; c < 16; ++c) f[c] = o[c];
           }
-        } else {  // LM_EPI_F32: [alpha | beta] halves; LM_EPI_F32_LD: one [M, ldo] fp32 matrix
-          float* dst = EPI == LM_EPI_F32_LD
-                           ? a.f32_a + (size_t)row * a.ldo + nb
-                           : (nb < LM_C ? a.f32_a + nb : a.f32_b + (nb - LM_C)) + (size_t)row * LM_C;
+        } else {
+          // fp32 outputs: one 32-column chunk = one 128-byte row of the staging buffer -> TMA store
+          // (LM_EPI_F32: columns [0,256) go to alpha through tmO_a, [256,512) to beta through tmO_b)
+          tc::named_bar_sync(2 + chalf, 128);  // the group's previous store has finished reading the buffer
+          tc::stage_row32(obuf, m, v);
+          fence_proxy_async();
+          tc::named_bar_sync(2 + chalf, 128);
+          if (store_leader) {
+            if (EPI == LM_EPI_F32 && nb >= LM_C) tc::tma_store_2d(&tmO_b, obuf, nb - LM_C, m0);
+            else tc::tma_store_2d(&tmO_a, obuf, nb, m0);
+            tc::tma_store_commit_and_wait_read();
+          }
+        }
+      }
+      if (EPI == LM_EPI_SPLIT || EPI == LM_EPI_RELU || EPI == LM_EPI_LRELU) {
+        // 64 bf16 columns of this group = one 128-byte staging row: hi plane first, then lo through the same buffer
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            reinterpret_cast<float4*>(dst)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        for (int plane = 0; plane < 2; ++plane) {
+          tc::named_bar_sync(2 + chalf, 128);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {  // 16-byte unit u = columns [8u, 8u+8) of the 64
+            const uint32_t* w = plane ? lw[u >> 2] : hw[u >> 2];
+            const int p = (u & 3) * 4;
+            *reinterpret_cast<uint4*>(obuf + m * 128 + ((u ^ (m & 7)) << 4)) = make_uint4(w[p], w[p + 1], w[p + 2], w[p + 3]);
+          }
+          fence_proxy_async();
+          tc::named_bar_sync(2 + chalf, 128);
+          if (store_leader) {
+            tc::tma_store_2d(plane ? &tmO_b : &tmO_a, obuf, n0 + chalf * 64, m0);
+            tc::tma_store_commit_and_wait_read();
+          }
         }
       }
     }
+    if (store_leader) tc::tma_store_wait_all();
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -412,6 +453,19 @@ static int lm_launch_geom(const Operand& a0, const Operand* a1, const StagePtrs&
   if ((rc = lm_make_map(&mA1l, s1.lo, s1.cols, rows, s1.ld))) return rc;
   if ((rc = lm_make_map(&mBh, w.hi, g.K, g.N, g.K))) return rc;
   if ((rc = lm_make_map(&mBl, w.lo, g.K, g.N, g.K))) return rc;
+  // output maps of the staged TMA-store epilogue (rows past `rows` are clipped by the map)
+  CUtensorMap mOa = mA0h, mOb = mA0l;
+  if (EPI == LM_EPI_SPLIT || EPI == LM_EPI_RELU || EPI == LM_EPI_LRELU) {
+    if ((rc = lm_make_map(&mOa, args.out_hi, args.ldo, rows, args.ldo))) return rc;
+    if ((rc = lm_make_map(&mOb, args.out_lo, args.ldo, rows, args.ldo))) return rc;
+  } else if (EPI == LM_EPI_F32 || EPI == LM_EPI_F32_LD) {
+    const int ld = EPI == LM_EPI_F32 ? LM_C : args.ldo;
+    const uint64_t dims[2] = {(uint64_t)ld, (uint64_t)rows};
+    const uint64_t str[1] = {(uint64_t)ld * 4};
+    const uint32_t box[2] = {32, LM_BM};
+    if ((rc = make_tensor_map_f32(&mOa, args.f32_a, 2, dims, str, box))) return rc;
+    if ((rc = make_tensor_map_f32(&mOb, EPI == LM_EPI_F32 ? args.f32_b : args.f32_a, 2, dims, str, box))) return rc;
+  }
   args.M = (int)rows;
   args.N = g.N;
   args.nkb0 = a0.cols / LM_BK;
@@ -427,7 +481,7 @@ static int lm_launch_geom(const Operand& a0, const Operand* a1, const StagePtrs&
   }
   const int64_t n_tiles = ((rows + LM_BM - 1) / LM_BM) * (g.N / LM_BN);
   const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-  fn<<<grid, LM_THREADS, LM_SMEM_BYTES, stream>>>(mA0h, mA0l, mA1h, mA1l, mBh, mBl, args);
+  fn<<<grid, LM_THREADS, LM_SMEM_BYTES, stream>>>(mA0h, mA0l, mA1h, mA1l, mBh, mBl, mOa, mOb, args);
   E3_CUDA(cudaGetLastError());
   return E3_OK;
 }
