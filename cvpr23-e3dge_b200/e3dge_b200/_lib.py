@@ -120,6 +120,8 @@ _PROTOTYPES = {
     "e3_torgb_fwd": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, _fp, c_int, c_int, c_int, c_int, _fp]),
     "e3_local_feature_query": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, _fp, c_int, c_int, c_int, c_int,
                                        c_int, c_int, _fp, _fp, _fp, _fp, _fp]),
+    "e3_local_feature_query_bwd": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, _fp, c_int, c_int, c_int, c_int, c_int,
+                                           c_int, _fp, _fp]),
     "e3_local_mlp_packed_bytes": (c_size_t, []),
     "e3_local_mlp_pack": (c_int, [POINTER(LocalMlpWeights), _fp, _fp]),
     "e3_local_mlp_workspace_bytes": (c_size_t, [c_int64]),
@@ -197,7 +199,7 @@ KERNELS_PER_CALL = {"e3_siren_pack": 1, "e3_film_fwd": 1, "e3_render_fwd": 1,
                     "e3_styled_conv3x3_fwd_presplit": 1, "e3_torgb_fwd": 1, "e3_styled_conv3x3_bwd": 7,
                     "e3_torgb_bwd": 2, "e3_modconv_styles_bwd": 1,
     "e3_pack_inversion_record": 1, "e3_ffma_peak_probe": 1, "e3_local_feature_query": 1,
-                    "e3_local_mlp_pack": 19, "e3_local_mlp_fwd": 7,
+                    "e3_local_feature_query_bwd": 1, "e3_local_mlp_pack": 19, "e3_local_mlp_fwd": 7,
                     "e3_tc_linear_pack": 1, "e3_tc_linear_fwd": 2}
 launch_count = 0
 

@@ -22,13 +22,48 @@ def _nhwc(feat):
     return out
 
 
+class _GatherFn(torch.autograd.Function):
+    """Channels-last feature map -> per-point features [B,N,C] with the adjoint for the map
+    (e3_local_feature_query / _bwd).  Points and calibration are not differentiated."""
+
+    @staticmethod
+    def forward(ctx, fmap, pts, calibs, xy, z, inside):
+        lib = _lib.load()
+        b, h, w, c = fmap.shape
+        n = pts.shape[2]
+        feats = torch.empty(b, n, c, device=fmap.device)
+        vp = _lib.vptr
+        _lib.check(lib.e3_local_feature_query(vp(fmap), vp(pts), pts.stride(0), pts.stride(1), pts.stride(2),
+                                              _lib.ptr(calibs), calibs.shape[-2] * 4, b, n, h, w, c, vp(feats),
+                                              _lib.ptr(xy), _lib.ptr(z), vp(inside), _lib.cur_stream()),
+                   "e3_local_feature_query")
+        ctx.save_for_backward(pts, calibs)
+        ctx.shape = (b, h, w, c)
+        return feats
+
+    @staticmethod
+    def backward(ctx, d_feats):
+        lib = _lib.load()
+        pts, calibs = ctx.saved_tensors
+        b, h, w, c = ctx.shape
+        d_feats = _lib.as_f32c(d_feats)
+        d_map = torch.empty(b, h, w, c, device=d_feats.device)
+        vp = _lib.vptr
+        _lib.check(lib.e3_local_feature_query_bwd(_lib.ptr(d_feats), vp(pts), pts.stride(0), pts.stride(1),
+                                                  pts.stride(2), _lib.ptr(calibs), calibs.shape[-2] * 4, b,
+                                                  pts.shape[2], h, w, c, _lib.ptr(d_map), _lib.cur_stream()),
+                   "e3_local_feature_query_bwd")
+        return d_map, None, None, None, None, None
+
+
 def query(points, calibs, im_feat=None, im_feat_nhwc=None, return_projection_only=False):
     """points [B,3,N] (any strides: a `.permute(0, 2, 1)` view of the renderer's [B,N,3] points is read in
     place), calibs [B,4,4] or [B,3,4], im_feat [B,C,H,W] (or `im_feat_nhwc` [B,H,W,C], to reuse one
     transposed map for several queries).  Returns the reference's dict: `proj_xy` [B,2,N], `depth` [B,1,N],
     `in_img` [B,N] bool and — unless `return_projection_only` — `feats` / `interp_feats` [B,C,N].
     `feats` is a view of a [B,N,C] buffer, so the `.permute(0, 2, 1)` the runner applies next
-    (e3dge_full_runner.py:229-230) is free.  Inference path: no autograd through the query."""
+    (e3dge_full_runner.py:229-230) is free.  When the feature map requires grad (stage-2 training of the local
+    branch) the gather carries its adjoint (e3_local_feature_query_bwd); points / calibs get no gradient."""
     lib = _lib.load()
     if not points.is_cuda:
         raise RuntimeError("e3dge_b200: CUDA tensor required (this framework has no CPU path)")
@@ -46,21 +81,37 @@ def query(points, calibs, im_feat=None, im_feat_nhwc=None, return_projection_onl
     inside = torch.empty(b, n, device=dev, dtype=torch.uint8)
     feats = fmap = None
     h = w = c = 4
+    pts = points.detach()
+    vp = _lib.vptr
     if not return_projection_only:
         if im_feat_nhwc is None:
             if im_feat is None:
                 raise RuntimeError("query: im_feat (or im_feat_nhwc) is required unless return_projection_only")
-            im_feat_nhwc = _nhwc(im_feat)
-        fmap = _lib.as_f32c(im_feat_nhwc)
-        if fmap.shape[0] != b:
-            raise RuntimeError("query: one feature map per image of the batch is required")
-        _, h, w, c = fmap.shape
-        feats = torch.empty(b, n, c, device=dev)
-    vp = _lib.vptr
-    pts = points.detach()
-    _lib.check(lib.e3_local_feature_query(vp(fmap), vp(pts), pts.stride(0), pts.stride(1), pts.stride(2),
-                                          _lib.ptr(calibs), calibs.shape[-2] * 4, b, n, h, w, c, vp(feats), _lib.ptr(xy),
-                                          _lib.ptr(z), vp(inside), _lib.cur_stream()), "e3_local_feature_query")
+            if torch.is_grad_enabled() and im_feat.requires_grad:  # training: the map's producer gets a gradient
+                from .stylesdf_model import _Permute
+                im_feat_nhwc = _Permute.apply(im_feat, True)
+            else:
+                im_feat_nhwc = _nhwc(im_feat)
+        if torch.is_grad_enabled() and im_feat_nhwc.requires_grad:
+            fmap = im_feat_nhwc if (im_feat_nhwc.dtype == torch.float32 and im_feat_nhwc.is_contiguous()) \
+                else im_feat_nhwc.float().contiguous()
+            if fmap.shape[0] != b:
+                raise RuntimeError("query: one feature map per image of the batch is required")
+            feats = _GatherFn.apply(fmap, pts, calibs, xy, z, inside)
+        else:
+            fmap = _lib.as_f32c(im_feat_nhwc.detach())
+            if fmap.shape[0] != b:
+                raise RuntimeError("query: one feature map per image of the batch is required")
+            _, h, w, c = fmap.shape
+            feats = torch.empty(b, n, c, device=dev)
+            _lib.check(lib.e3_local_feature_query(vp(fmap), vp(pts), pts.stride(0), pts.stride(1), pts.stride(2),
+                                                  _lib.ptr(calibs), calibs.shape[-2] * 4, b, n, h, w, c, vp(feats),
+                                                  _lib.ptr(xy), _lib.ptr(z), vp(inside), _lib.cur_stream()),
+                       "e3_local_feature_query")
+    else:
+        _lib.check(lib.e3_local_feature_query(None, vp(pts), pts.stride(0), pts.stride(1), pts.stride(2),
+                                              _lib.ptr(calibs), calibs.shape[-2] * 4, b, n, h, w, c, None, _lib.ptr(xy),
+                                              _lib.ptr(z), vp(inside), _lib.cur_stream()), "e3_local_feature_query")
     out = {"proj_xy": xy, "depth": z, "in_img": inside.bool()}
     if feats is not None:
         f = feats.permute(0, 2, 1)
@@ -77,7 +128,8 @@ def install(net_local):
 
     def patched(points, calibs, feat_key=None, return_eikonal=False, transforms=None, labels=None,
                 return_feat_only=False, im_feat=None, return_projection_only=False):
-        fast = (transforms is None and not return_eikonal and points.is_cuda and not torch.is_grad_enabled()
+        fast = (transforms is None and not return_eikonal and points.is_cuda
+                and not (torch.is_grad_enabled() and points.requires_grad)
                 and (return_projection_only or im_feat is not None))
         if not fast:
             return original(points, calibs, feat_key, return_eikonal=return_eikonal, transforms=transforms,

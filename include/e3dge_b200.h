@@ -421,6 +421,15 @@ int e3_local_feature_query(const float* feat_nhwc, const float* points, int64_t 
                            float* feats, float* proj_xy, float* depth, unsigned char* in_img,
                            void* stream);
 
+/* Adjoint of e3_local_feature_query with respect to the feature map: d_feat_nhwc [B,H,W,C] (overwritten) =
+ * scatter-add of d_feats [B,N,C] over the four bilinear taps of every point (the reference's
+ * op/grid_sample_gradfix.py backward; float atomics, so the summation order is not fixed).  Same point /
+ * calibration arguments as the forward call. */
+int e3_local_feature_query_bwd(const float* d_feats, const float* points, int64_t pts_batch_stride,
+                               int64_t pts_coord_stride, int64_t pts_point_stride, const float* calibs,
+                               int calib_stride, int batch, int n_points, int h, int w, int c,
+                               float* d_feat_nhwc, void* stream);
+
 /* ----------------------------------------------------------------------------------
  * Local branch, rest of SURVEY.md section 8(f) row 1: the per-sample MLP tail between the feature query
  * and the renderer's texture modulation — `Fuse_sft_MLP(257, 256)` of the runner

@@ -82,3 +82,28 @@ def test_install_patches_a_reference_style_module():
                         return_feat_only=True, im_feat=t("feat"))
         assert rel_linf(out["feats"].cpu(), torch.from_numpy(z["neg_z.feats"])) < 1e-5
         assert net.query(t("points"), t("calibs"), "ref_view") == "original"   # stored-feature path: untouched
+
+
+def test_query_backward_to_the_feature_map_matches_the_oracle_autograd():
+    """Stage-2 training reaches netLocal's hourglass filter through the gather: d loss / d feature map from
+    e3_local_feature_query_bwd against autograd through the oracle's bilinear sampling (float64)."""
+    from e3dge_b200 import local_query as lq
+    from e3dge_b200.frontend import generate_camera_params
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(2, 16, 12, 20, generator=g)
+    pts = (torch.rand(2, 3, 300, generator=g) - 0.5) * 0.3
+    pts[:, :, -40:] *= 6.0  # a few far outside the frustum: zero padding, no gradient
+    calibs = generate_camera_params(64, torch.device("cpu"), 2, return_calibs=True, generator=g)["calibs"]
+    cot = torch.randn(2, 16, 300, generator=g)
+    f64 = feat.double().requires_grad_(True)
+    ref = LQ.local_feature_query(pts.double(), calibs.double(), f64)
+    gref, = torch.autograd.grad((ref["feats"] * cot.double()).sum(), [f64])
+    fc = feat.cuda().requires_grad_(True)
+    out = lq.query(pts.cuda(), calibs.cuda(), im_feat=fc)
+    assert out["feats"].requires_grad
+    ggot, = torch.autograd.grad((out["feats"] * cot.cuda()).sum(), [fc])
+    assert rel_linf(out["feats"].detach().cpu(), ref["feats"].detach()) < 1e-5
+    assert rel_linf(ggot.cpu(), gref) < 1e-5
+    # no graph when nothing asks for one
+    with torch.no_grad():
+        assert not lq.query(pts.cuda(), calibs.cuda(), im_feat=fc)["feats"].requires_grad
