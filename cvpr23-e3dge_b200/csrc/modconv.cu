@@ -658,7 +658,7 @@ extern "C" int e3_modconv_styles(const float* latent, int64_t latent_stride, con
 
 // packed image: [fp32 GEMM-major (cout*cin*9 floats)] [bf16 hi K-major] [bf16 lo K-major]
 extern "C" size_t e3_conv_packed_bytes(int cout, int cin) {
-  return (size_t)cout * cin * 9 * (sizeof(float) + 2 * 2);
+  return (size_t)cout * cin * 9 * sizeof(float) + tc_conv_packed_bf16_bytes(cout, cin);
 }
 static inline const void* packed_bf16_part(const void* packed, int cout, int cin) {
   return static_cast<const char*>(packed) + (size_t)cout * cin * 9 * sizeof(float);
@@ -679,6 +679,18 @@ extern "C" int e3_conv_pack_weight(const float* weight, int cout, int cin, int u
                              const_cast<void*>(packed_bf16_part(packed, cout, cin)), as_stream(stream));
 }
 
+// rows of the x-pair view: s2[b] = [s[b] | s[b]], d2[b] = [d[b] | d[b]], bias2 = [bias | bias] (32 -> 64 columns)
+__global__ void dup_pair_kernel(const float* __restrict__ s, const float* __restrict__ d,
+                                const float* __restrict__ bias, int batch, float* s2, float* d2, float* b2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch * 64) {
+    const int b = i >> 6, c = i & 31;
+    s2[i] = s[b * 32 + c];
+    d2[i] = d[b * 32 + c];
+  }
+  if (i < 64 && bias) b2[i] = bias[i & 31];
+}
+
 static bool use_tensor_cores(uint32_t flags, int batch, int h, int w, int cin, int n) {
   if (flags & E3_CONV_FP32_CUDA_CORES) return false;
   return tc_conv_supported(batch, h, w, cin, n);
@@ -689,7 +701,8 @@ static bool use_tensor_cores(uint32_t flags, int batch, int h, int w, int cin, i
 //                        path, always smaller)] [xs_hi | xs_lo on the zero-padded grid B*(H+1)*(W+1)*cin]
 extern "C" size_t e3_styled_conv_scratch_bytes(int batch, int h, int w, int cin, int cout,
                                                int upsample) {
-  if (!upsample) return tc_conv_split_bytes(batch, h, w, cin) + 256;
+  // (+ the duplicated s / d / bias rows of the x-pair view of a 32 -> 32 conv)
+  if (!upsample) return tc_conv_split_bytes(batch, h, w, cin) + 256 + ((size_t)2 * batch + 1) * 64 * sizeof(float) + 256;
   size_t g = (size_t)batch * h * w * 9 * cout * sizeof(float);
   const size_t t = tc_upconv_t_bytes(batch, h, w, cout);
   if (t > g) g = t;
@@ -720,8 +733,24 @@ extern "C" int e3_styled_conv3x3_fwd(const float* x, const void* wpacked, const 
   a.mode = act_bias ? 1 : 2, a.d = d, a.noise = noise, a.noise_bstride = noise_batch_stride;
   a.noise_w = noise_w, a.act_bias = act_bias;
   const bool tcore = use_tensor_cores(flags, batch, h, w, cin, cout);
-  E3_REQUIRE(tcore || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
+  const bool pairx = !tcore && !(flags & E3_CONV_FP32_CUDA_CORES) && tc_conv_pairx_supported(batch, h, w, cin, cout);
+  E3_REQUIRE(tcore || pairx || !(flags & E3_CONV_TENSOR_CORES), E3_ERR_UNSUPPORTED,
              "e3_styled_conv3x3_fwd: E3_CONV_TENSOR_CORES requested for an unsupported shape");
+  if (pairx) {
+    // 32 -> 32 at 1024^2: two x-adjacent pixels form one 64-channel operand row (same memory), the 3x3 kernel
+    // becomes a block-structured 3 x 3-pair-tap kernel (half of its 64 x 64 blocks' entries are zero)
+    E3_REQUIRE(scratch && scratch_bytes >= e3_styled_conv_scratch_bytes(batch, h, w, cin, cout, 0),
+               E3_ERR_SCRATCH, "e3_styled_conv3x3_fwd: scratch too small");
+    char* split = reinterpret_cast<char*>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    float* dup = reinterpret_cast<float*>(
+        ((uintptr_t)(split + tc_conv_split_bytes(batch, h, w, cin)) + 255) & ~(uintptr_t)255);
+    float *s2 = dup, *d2 = dup + (size_t)batch * 64, *b2 = dup + (size_t)2 * batch * 64;
+    dup_pair_kernel<<<(batch * 64 + 255) / 256 + 1, 256, 0, as_stream(stream)>>>(s, d, act_bias, batch, s2, d2, b2);
+    E3_CUDA(cudaGetLastError());
+    a.s = s2, a.d = d2, a.act_bias = act_bias ? b2 : nullptr;
+    a.W = w / 2, a.Cin = 64, a.N = 64, a.pairx = 1;
+    return tc_conv_launch(a, 9, packed_bf16_part(wpacked, cout, cin), split, as_stream(stream));
+  }
   if (tcore) {
     E3_REQUIRE(scratch && scratch_bytes >= e3_styled_conv_scratch_bytes(batch, h, w, cin, cout, 0),
                E3_ERR_SCRATCH, "e3_styled_conv3x3_fwd: scratch too small");

@@ -22,12 +22,19 @@ struct ConvGemmArgs {
   // reads plane (ky&1, kx&1) at (y + (ky>>1), x + (kx>>1)) — the stride-2 gather of the up-conv
   // backward as nine dense shifted reads (tensor-core path only, operands pre-split by the caller)
   int planar;
+  // 1: x-pair view of a 32 -> 32 conv (tensor-core path): the operands are [B][H][W/2][2 pixels x 32 ch] with
+  // W here = W/2, Cin = N = 64 and a block-structured weight image (tc_conv_pack_weight layout 4); the
+  // epilogue's only difference is the noise, which belongs to pixel 2*x + (column >> 5)
+  int pairx;
 };
 
 bool tc_conv_supported(int B, int H, int W, int Cin, int N);
 size_t tc_conv_split_bytes(int B, int H, int W, int Cin);
 int tc_conv_pack_weight(const float* weight, int cout, int cin, int upsample, float scale,
                         void* packed_bf16, cudaStream_t stream);
+// 32 -> 32 plain convs run on the tensor cores through the x-pair view (ConvGemmArgs::pairx)
+bool tc_conv_pairx_supported(int B, int H, int W, int Cin, int N);
+size_t tc_conv_packed_bf16_bytes(int cout, int cin);
 int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, void* split_scratch,
                    cudaStream_t stream);
 // same without the modulate+split pass: xs_hi / xs_lo are the caller's bf16 operand halves

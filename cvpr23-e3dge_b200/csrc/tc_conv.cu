@@ -105,10 +105,24 @@ __constant__ int kUpTapOrder[9] = {0, 2, 6, 8, 1, 7, 3, 5, 4};
 __global__ void conv_pack_bf16_kernel(const float* __restrict__ w, int cout, int cin, int upsample,
                                       float scale, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo) {
-  const int64_t total = (int64_t)cout * cin * 9;
+  const int64_t total = upsample == 4 ? (int64_t)64 * 576 : (int64_t)cout * cin * 9;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int o, ci, tap;
+    if (upsample == 4) {
+      // x-pair view of a 32 -> 32 conv: rows n' = p_out*32 + co, columns k' = tap'*64 + p_in*32 + ci with
+      // tap' = (dy+1)*3 + (pair shift + 1); the entry is W[co][ci][dy+1][kx] for kx = 2*shift + p_in - p_out + 1
+      // when that is a tap of the 3x3 kernel, else zero
+      const int kq = (int)(idx % 576), np = (int)(idx / 576);
+      const int tq = kq >> 6, r = kq & 63, p_in = r >> 5, p_out = np >> 5;
+      ci = r & 31, o = np & 31;
+      const int kx = 2 * (tq % 3 - 1) + p_in - p_out + 1, ky = tq / 3;
+      __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
+      if (kx >= 0 && kx <= 2) tc::split_bf16(scale * w[((size_t)o * 32 + ci) * 9 + ky * 3 + kx], h, l);
+      hi[idx] = h;
+      lo[idx] = l;
+      continue;
+    }
     if (upsample >= 2) {
       const int k = (int)(idx % ((int64_t)9 * cout));
       ci = (int)(idx / ((int64_t)9 * cout));
@@ -171,7 +185,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles_n = a.N / TC_BN;
+  // narrow layers (N = 64 / 32: the 512^2 / 1024^2 stages of a size-1024 decoder): one n-tile whose MMAs are
+  // issued N columns wide and whose weight box holds N rows; accumulator columns past N do not exist
+  const int nbox = a.N < TC_BN ? a.N : TC_BN;
+  const uint32_t stage_tx = 2 * TC_TILE_BYTES + 2 * nbox * 128;
+  const int n_tiles_n = (a.N + TC_BN - 1) / TC_BN;
   const int n_tiles = t.tiles_x * t.tiles_y * t.tiles_b * n_tiles_n;
   const int kpt = a.Cin / TC_BK, nkb = TAPS * kpt;
 
@@ -219,7 +237,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             dx = kx >> 1, dy = ky >> 1, bc = ((ky & 1) * 2 + (kx & 1)) * a.B + b0;
           }
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[stage], stage_tx);
           uint8_t* st = smem + stage * TC_STAGE_BYTES;
           tc::tma_load_4d(st, &tmA_hi, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, bc);
           tc::tma_load_4d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, x0 + dx, y0 + dy, bc);
@@ -234,7 +252,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, TC_BN);
+      const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, nbox);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1, use = it >> 1;
@@ -281,21 +299,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t buf = it & 1, use = it >> 1;
       const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
       const bool valid = b < a.B;
-      const int p = y * a.W + x;
-      const float nz = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
+      const int p = a.pairx ? 2 * (y * a.W + x) : y * a.W + x;  // pair view: first of the row's two pixels
+      const float nz0 = (a.mode == 1 && valid) ? nw * a.noise[(size_t)b * a.noise_bstride + p] : 0.f;
+      const float nz1 = (a.mode == 1 && valid && a.pairx) ? nw * a.noise[(size_t)b * a.noise_bstride + p + 1] : 0.f;
       mbar_wait(&acc_full[buf], use & 1);
       tc::fence_after_thread_sync();
       constexpr int kChunksPerWarp = TC_BN / 32 / (TC_EPI_WARPS / 4);
 #pragma unroll 1
       for (int chunk = chalf * kChunksPerWarp; chunk < (chalf + 1) * kChunksPerWarp; ++chunk) {
         float v[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
+        const bool live = chunk * 32 < nbox;  // (uniform over the warp group)
+        if (live) tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
         if (chunk == (chalf + 1) * kChunksPerWarp - 1) {  // this warp's share is read: tell the MMA warp
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (!live) continue;
         const int nb = n0 + chunk * 32;
+        const float nz = (a.pairx && (chunk & 1)) ? nz1 : nz0;  // pair view: columns [32,64) are the odd pixel
         if (valid && a.mode == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -640,7 +662,9 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + TC_ACC_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles_n = a.N / TC_BN;
+  const int nbox = a.N < TC_BN ? a.N : TC_BN;  // narrow layers: see tc_conv_kernel
+  const uint32_t stage_tx = 2 * TC_TILE_BYTES + 2 * nbox * 128;
+  const int n_tiles_n = (a.N + TC_BN - 1) / TC_BN;
   const int m_tiles = (a.Mp + TC_BM - 1) / TC_BM;
   const int n_tiles = 4 * m_tiles * n_tiles_n;
   const int kpt = a.Cin / TC_BK;
@@ -697,7 +721,7 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
           else shift = t;  // p == 2: kx = 0, 2;  p == 3: the centre tap
           for (int kc = 0; kc < kpt; ++kc) {
             mbar_wait(&empty[stage], phase_bit ^ 1);
-            mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+            mbar_arrive_expect_tx(&full[stage], stage_tx);
             uint8_t* st = smem + stage * TC_STAGE_BYTES;
             tc::tma_load_2d(st, &tmA_hi, &full[stage], kc * TC_BK, m0 - shift);
             tc::tma_load_2d(st + TC_TILE_BYTES, &tmA_lo, &full[stage], kc * TC_BK, m0 - shift);
@@ -713,7 +737,7 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, TC_BN);
+      const uint32_t idesc = tc::make_idesc_bf16_f32(TC_BM, nbox);
       uint32_t stage = 0, phase_bit = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         int p, m0, n0, ntaps, tq0;
@@ -765,12 +789,14 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
 #pragma unroll 1
       for (int chunk = chalf * kChunksPerWarp; chunk < (chalf + 1) * kChunksPerWarp; ++chunk) {
         float v[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
+        const bool live = chunk * 32 < nbox;
+        if (live) tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_BN + chunk * 32, v);
         if (chunk == (chalf + 1) * kChunksPerWarp - 1) {
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (!live) continue;
         // staging buffer -> TMA tensor store into T[phase] (rows past Mp are clipped by the tensor map)
         tc::named_bar_sync(2 + chalf, 128);
         tc::stage_row32(obuf, row, v);
@@ -789,8 +815,11 @@ tc_upconv_phase_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
   if (warp == 1) tc::tmem_dealloc(tmem_base, TC_ACC_BUFS * TC_BN);
 }
 
+// output widths of the tensor-core kernels: whole 128-column tiles, or one narrow tile of 64 / 32 columns
+static bool tc_n_supported(int n) { return n > 0 && (n % TC_BN == 0 || n == 64 || n == 32); }
+
 bool tc_upconv_supported(int B, int H, int W, int Cin, int cout) {
-  return B > 0 && H > 0 && W > 0 && Cin % TC_BK == 0 && cout % TC_BN == 0 &&
+  return B > 0 && H > 0 && W > 0 && Cin % TC_BK == 0 && tc_n_supported(cout) &&
          (int64_t)B * (H + 1) * (W + 1) < (1ll << 30);
 }
 size_t tc_upconv_split_bytes(int B, int H, int W, int Cin) {
@@ -806,7 +835,7 @@ int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, 
                            const void* packed_bf16, void* split_scratch, float* t_out, cudaStream_t stream) {
   E3_REQUIRE(tc_upconv_supported(B, H, W, Cin, cout), E3_ERR_UNSUPPORTED,
              "tensor-core up-conv: unsupported shape B=%d H=%d W=%d Cin=%d cout=%d (needs Cin %% 64 == 0, "
-             "cout %% 128 == 0)", B, H, W, Cin, cout);
+             "cout %% 128 == 0 or cout in {32, 64})", B, H, W, Cin, cout);
   const int64_t Mp = (int64_t)B * (H + 1) * (W + 1);
   __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
   __nv_bfloat16* xs_lo = xs_hi + Mp * Cin;
@@ -826,7 +855,7 @@ int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, 
   const uint32_t abox[2] = {(uint32_t)TC_BK, (uint32_t)TC_BM};
   const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)cout};
   const uint64_t bstr[1] = {(uint64_t)K * 2};
-  const uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)TC_BN};
+  const uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)(cout < TC_BN ? cout : TC_BN)};
   int rc;
   if ((rc = make_tensor_map_bf16(&tmA_hi, xs_hi, 2, adims, astr, abox))) return rc;
   if ((rc = make_tensor_map_bf16(&tmA_lo, xs_lo, 2, adims, astr, abox))) return rc;
@@ -845,7 +874,7 @@ int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, 
   const uint32_t obox[3] = {32, (uint32_t)TC_BM, 1};
   if ((rc = make_tensor_map_f32(&tmOut, t_out, 3, odims, ostr, obox))) return rc;
   UpPhaseArgs a{t_out, (int)Mp, cout, Cin, W + 1};
-  const int group = 4 * (cout / TC_BN);  // tiles that share one m-tile: all phases x n-tiles
+  const int group = 4 * ((cout + TC_BN - 1) / TC_BN);  // tiles that share one m-tile: all phases x n-tiles
   const int n_tiles = group * (int)((Mp + TC_BM - 1) / TC_BM);
   int grid = sm_count() / group * group;  // multiple of the group: the phase rotation stays a bijection
   if (grid < group) grid = group;
@@ -857,18 +886,28 @@ int tc_upconv_phase_launch(const float* x, const float* s, int B, int H, int W, 
 
 bool tc_conv_supported(int B, int H, int W, int Cin, int N) {
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-  return B > 0 && pow2(W) && pow2(H) && W >= 8 && H * W >= 64 && Cin % TC_BK == 0 && N % TC_BN == 0;
+  return B > 0 && pow2(W) && pow2(H) && W >= 8 && H * W >= 64 && Cin % TC_BK == 0 && tc_n_supported(N);
 }
 
 size_t tc_conv_split_bytes(int B, int H, int W, int Cin) {
   return (size_t)B * H * W * Cin * 2 * sizeof(__nv_bfloat16);
 }
 
+bool tc_conv_pairx_supported(int B, int H, int W, int Cin, int N) {
+  return Cin == 32 && N == 32 && W % 2 == 0 && tc_conv_supported(B, H, W / 2, 64, 64);
+}
+size_t tc_conv_packed_bf16_bytes(int cout, int cin) {
+  if (cout == 32 && cin == 32) return (size_t)64 * 576 * 2 * 2;  // x-pair image of the plain conv (layout 0)
+  return (size_t)cout * cin * 9 * 2 * 2;
+}
+
 int tc_conv_pack_weight(const float* weight, int cout, int cin, int upsample, float scale,
                         void* packed_bf16, cudaStream_t stream) {
+  // a 32 -> 32 plain conv has no K-block of 64 input channels: its tensor-core image is the x-pair view
+  if (upsample == 0 && cout == 32 && cin == 32) upsample = 4;
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(packed_bf16);
-  __nv_bfloat16* lo = hi + (size_t)cout * cin * 9;
-  const int64_t total = (int64_t)cout * cin * 9;
+  const int64_t total = upsample == 4 ? (int64_t)64 * 576 : (int64_t)cout * cin * 9;
+  __nv_bfloat16* lo = hi + total;
   int blocks = (int)((total + 255) / 256);
   if (blocks > sm_count() * 32) blocks = sm_count() * 32;
   conv_pack_bf16_kernel<<<blocks, 256, 0, stream>>>(weight, cout, cin, upsample, scale, hi, lo);
@@ -883,7 +922,7 @@ int tc_conv_launch(const ConvGemmArgs& a, int taps, const void* packed_bf16, voi
                    cudaStream_t stream) {
   E3_REQUIRE(tc_conv_supported(a.B, a.H, a.W, a.Cin, a.N), E3_ERR_UNSUPPORTED,
              "tensor-core conv: unsupported shape B=%d H=%d W=%d Cin=%d N=%d (needs power-of-two "
-             "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0)", a.B, a.H, a.W, a.Cin, a.N);
+             "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0 or N in {32, 64})", a.B, a.H, a.W, a.Cin, a.N);
   const size_t n_act = (size_t)a.B * a.H * a.W * a.Cin;
   __nv_bfloat16* xs_hi = static_cast<__nv_bfloat16*>(split_scratch);
   __nv_bfloat16* xs_lo = xs_hi + n_act;
@@ -901,7 +940,7 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
                             const void* xs_lo, cudaStream_t stream) {
   E3_REQUIRE(tc_conv_supported(a.B, a.H, a.W, a.Cin, a.N), E3_ERR_UNSUPPORTED,
              "tensor-core conv: unsupported shape B=%d H=%d W=%d Cin=%d N=%d (needs power-of-two "
-             "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0)", a.B, a.H, a.W, a.Cin, a.N);
+             "H, W >= 8, Cin %% 64 == 0, N %% 128 == 0 or N in {32, 64})", a.B, a.H, a.W, a.Cin, a.N);
   E3_REQUIRE(!a.planar || taps == 9, E3_ERR_BAD_ARG, "tensor-core conv: planar operands need 9 taps");
   TcTile t;
   t.bw = a.W < 128 ? a.W : 128;
@@ -922,7 +961,7 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
   const uint32_t abox[4] = {(uint32_t)TC_BK, (uint32_t)t.bw, (uint32_t)t.bh, (uint32_t)t.bb};
   const uint64_t bdims[2] = {(uint64_t)K, (uint64_t)a.N};
   const uint64_t bstr[1] = {(uint64_t)K * 2};
-  const uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)TC_BN};
+  const uint32_t bbox[2] = {(uint32_t)TC_BK, (uint32_t)(a.N < TC_BN ? a.N : TC_BN)};
   int rc;
   if ((rc = make_tensor_map_bf16(&tmA_hi, xs_hi, 4, adims, astr, abox))) return rc;
   if ((rc = make_tensor_map_bf16(&tmA_lo, xs_lo, 4, adims, astr, abox))) return rc;
@@ -957,7 +996,7 @@ int tc_conv_launch_presplit(const ConvGemmArgs& a, int taps, const void* packed_
     E3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set[which] = true;
   }
-  const int n_tiles = t.tiles_x * t.tiles_y * t.tiles_b * (a.N / TC_BN);
+  const int n_tiles = t.tiles_x * t.tiles_y * t.tiles_b * ((a.N + TC_BN - 1) / TC_BN);
   dim3 grid(n_tiles < sm_count() ? n_tiles : sm_count());
   if (taps == 9)
     tc_conv_kernel<9><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmOut, a, t);

@@ -275,6 +275,9 @@ def _set_backend(module, backend):
     (256, 512, 64, 1, False), (512, 256, 64, 1, True),    # conv1 / first up-conv of the 256^2 decoder
     (128, 128, 256, 1, False),                            # last conv: 128-wide row tiles
     (64, 128, 12, 2, True), (64, 256, 5, 3, True),        # up-conv on maps that are not powers of two (odd too)
+    # the narrow 512^2 / 1024^2 stages of a size-1024 decoder (stylesdf_model.py:614-624): one 64- / 32-column tile
+    (64, 64, 32, 2, False), (128, 64, 16, 2, True), (64, 32, 16, 3, True), (128, 32, 8, 1, False),
+    (32, 32, 32, 2, False), (32, 32, 16, 3, False),        # 32 -> 32 through the x-pair view
 ])
 def test_tensor_core_conv_vs_fp32_path_and_oracle(cin, cout, hw, batch, up):
     from e3dge_b200.stylesdf_model import StyledConv
