@@ -322,6 +322,11 @@ def run_ours(args):
     if rank == 0:
         line.update(kernel_roofline(G, resident, dev, flush, args))
         line["train_step"] = train_step_timing(G, resident, flush, args)
+        if world == 1 and not args.no_size1024:
+            try:
+                line["size_1024"] = size1024_timing(dev, flush, args)
+            except Exception as exc:
+                line["size_1024"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and not args.no_full_frame:
             try:
                 line["full_frame"] = full_frame_timing(G, dev, flush, args, world, sync_all)
@@ -552,6 +557,47 @@ def full_frame_timing(G, dev, flush, args, world, sync_all):
             "d2h_bytes_per_step": img_out.numel() * 4}
 
 
+def size1024_timing(dev, flush, args):
+    """Secondary figure: the same generator pass at --size 1024, the output size every shipped E3DGE script runs
+    (demo_view_synthesis.sh:35-36): four up-sampling stages, the last two 64 and 32 channels wide at 512^2 / 1024^2
+    (stylesdf_model.py:614-624; narrow tensor-core tiles and the x-pair view of the 32 -> 32 conv)."""
+    import synthetic_inputs as P
+    from helpers import decoder_layout, synthetic_state_dict
+    from e3dge_b200 import model_options, rendering_options
+    from e3dge_b200.graphed import GraphedCall
+    from e3dge_b200.stylesdf_model import G_pred_latents
+    size, batch = 1024, 4
+    sd = synthetic_state_dict(size, RES, SEED, "sharp")
+    G = G_pred_latents(model_options(size=size, renderer_spatial_output_dim=RES), rendering_options(N_samples=N_SAMPLES),
+                       full_pipeline=True).eval()
+    G.load_state_dict(sd, strict=True)
+    G = G.to(dev)
+    inp = {k: v.to(dev) for k, v in P.make_inputs(SEED, batch, decoder_layout(size, RES), RES).items()}
+
+    def core():
+        with torch.no_grad():
+            return G([inp["w"], inp["w_dec"]], inp["cam_poses"], inp["focal"], inp["near"], inp["far"],
+                     input_is_latent=True, randomize_noise=True)
+    call = GraphedCall(core)
+    n = max(3, min(args.steps, 10))
+    for _ in range(3):
+        call()
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        call()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = statistics.median(ts)
+    return {"what": "generator pass at size 1024 (64^2 x 24 render + 4 up-sampling stages), batch %d, CUDA-graph replay" % batch,
+            "ms_per_step": ms, "frames_per_s": batch / (ms / 1e3),
+            "decoder_tflops_algorithmic": 62.8e9 * 2 * batch / (ms / 1e3) / 1e12}
+
+
 def train_step_timing(G, inp, flush, args):
     """Secondary figure (not the headline metric): the same batch through the generator with the
     backward kernels — forward writing the stash, then dL/d(w+), dL/d(decoder latent) of an image
@@ -683,6 +729,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact-fp32", action="store_true", help="skip the exact-fp32 back-end timing")
     ap.add_argument("--no-local-branch", action="store_true", help="skip the local-branch frame timing")
+    ap.add_argument("--no-size1024", action="store_true", help="skip the size-1024 generator timing")
     ap.add_argument("--no-full-frame", action="store_true", help="skip the encoder -> render -> decode frame timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
