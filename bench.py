@@ -198,12 +198,28 @@ def run_ours(args):
                     return_sdf=True)
             par.pack_records(static["w"], static["w_dec"], out["gen_imgs"], target, out=rec_local)
         return out
+    gather_in_graph = False
+
+    def core_with_gather():
+        out = core()
+        par.gather_records(rec_local, out=rec_all, equal_shards=True)
+        return out
     try:
         if os.environ.get("E3DGE_BENCH_EAGER"):  # profiling aid: every kernel launched from Python, in order
             raise RuntimeError("E3DGE_BENCH_EAGER")
-        gcall = GraphedCall(core)
-        launch_mode = ("CUDA-graph replay of G_pred_latents.forward + record kernel "
-                       "(e3dge_b200.graphed.GraphedCall); `eager` = the same step launched from Python")
+        gcall = None
+        if world > 1 and not os.environ.get("E3DGE_BENCH_GATHER_OUTSIDE"):
+            try:  # the step's one collective recorded into the same graph (NCCL is capturable)
+                gcall = GraphedCall(core_with_gather)
+                gather_in_graph = True
+            except Exception:
+                torch.cuda.synchronize()
+                gcall = None
+        if gcall is None:
+            gcall = GraphedCall(core)
+        launch_mode = ("CUDA-graph replay of G_pred_latents.forward + record kernel"
+                       + (" + the NCCL all-gather of the records" if gather_in_graph else "")
+                       + " (e3dge_b200.graphed.GraphedCall); `eager` = the same step launched from Python")
     except Exception as exc:  # capture refused (e.g. a profiler that forbids it): measure the eager step
         torch.cuda.synchronize()
 
@@ -218,7 +234,7 @@ def run_ours(args):
 
     def step_graph():
         out = gcall()
-        if world > 1:
+        if world > 1 and not gather_in_graph:
             par.gather_records(rec_local, out=rec_all, equal_shards=True)
         return out
 
