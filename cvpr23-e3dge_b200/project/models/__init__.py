@@ -1,1 +1,1 @@
-from . import op, stylesdf_model  # noqa: F401
+from . import encoders, helper_modules, op, stylesdf_model  # noqa: F401

@@ -1,1 +1,1 @@
-from . import volume_renderer  # noqa: F401
+from . import camera_utils, misc_utils, volume_renderer  # noqa: F401

@@ -89,6 +89,13 @@ def test_reference_import_paths_resolve_to_this_package():
             "from project.utils.volume_renderer import VolumeFeatureRenderer, SirenGenerator; "
             "from project.models.stylesdf_model import G_pred_latents, Generator, Decoder; "
             "from project.models.op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d; "
+            "from project.utils.volume_renderer import SirenLocalGlobal; "
+            "from project.models.helper_modules.sft import Fuse_sft_MLP; "
+            "from project.models.helper_modules.resnetfc import ResnetBlockFC; "
+            "from project.utils.misc_utils import PosEncoding; "
+            "from project.models.encoders.fpn_encoders import HybridGradualStyleEncoder_V2; "
+            "from project.models.stylesdf_model import VolumeRenderDiscriminator; "
+            "from project.utils.camera_utils import generate_camera_params; "
             "import e3dge_b200.stylesdf_model as m; assert G_pred_latents is m.G_pred_latents; "
             "print('ok')" % PKG)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
