@@ -208,8 +208,8 @@ def run_ours(args):
         if os.environ.get("E3DGE_BENCH_EAGER"):  # profiling aid: every kernel launched from Python, in order
             raise RuntimeError("E3DGE_BENCH_EAGER")
         gcall = None
-        if world > 1 and not os.environ.get("E3DGE_BENCH_GATHER_OUTSIDE"):
-            try:  # the step's one collective recorded into the same graph (NCCL is capturable)
+        if world > 1 and os.environ.get("E3DGE_BENCH_GATHER_IN_GRAPH"):
+            try:  # opt-in experiment: the step's one collective recorded into the same graph
                 gcall = GraphedCall(core_with_gather)
                 gather_in_graph = True
             except Exception:
