@@ -209,7 +209,10 @@ def run_ours(args):
             raise RuntimeError("E3DGE_BENCH_EAGER")
         gcall = None
         if world > 1 and os.environ.get("E3DGE_BENCH_GATHER_IN_GRAPH"):
-            try:  # opt-in experiment: the step's one collective recorded into the same graph
+            # opt-in experiment: the step's one collective recorded into the same graph.  Works (profiles/
+            # r02_scale.txt) but NCCL then waits at communicator teardown for the graph that captured it, so the
+            # processes hang at exit while the graph object is alive — off unless asked for.
+            try:
                 gcall = GraphedCall(core_with_gather)
                 gather_in_graph = True
             except Exception:
@@ -281,7 +284,7 @@ def run_ours(args):
         # the same step on the exact-fp32 back ends (FFMA renderer, FFMA implicit-GEMM convs): every
         # contraction in plain fp32 like the reference, whole step and end to end
         exact = None
-        if not args.no_exact_fp32:
+        if not args.no_exact_fp32 and world == 1:  # (secondary arm: single-GPU runs only)
             set_backends(G, "fp32")
             try:
                 gcall32 = GraphedCall(core)
