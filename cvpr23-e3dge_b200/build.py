@@ -20,6 +20,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
          "--expt-relaxed-constexpr"]
+if os.environ.get("E3_TRACE"):  # measurement build: clock64 trace hook of the render kernel (profiles/trace_render.py)
+    FLAGS.append("-DE3_TRACE")
 
 
 def sources():

@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """clock64() timeline of one tile of the tensor-core render kernel (CTA 0, second tile).
-Run under gpurun:  E3DGE_RENDER_CLUSTER=1 python profiles/trace_render.py"""
+The trace hook is compiled only into a measurement build (round 2: it used to be a live environment lookup in the
+production launch path): run under gpurun as
+    E3_TRACE=1 python cvpr23-e3dge_b200/build.py --force && python profiles/trace_render.py
+and rebuild without E3_TRACE afterwards (a fresh gpurun box starts from the repository's own library)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "cvpr23-e3dge_b200"), os.path.join(ROOT, "tests")]

@@ -100,3 +100,45 @@ def test_reference_import_paths_resolve_to_this_package():
             "print('ok')" % PKG)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_packed_weight_images_are_invalidated_by_every_route_that_changes_weights():
+    """in-place `.data` updates do not bump tensor versions, so the packed kernel images carry an epoch
+    that load_state_dict / .to() / train() / accumulate() / invalidate_packed() advance."""
+    import e3dge_b200
+    from e3dge_b200 import _lib, model_options, rendering_options
+    from e3dge_b200.stylesdf_model import G_pred_latents
+    G = G_pred_latents(model_options(size=64, renderer_spatial_output_dim=16), rendering_options())
+    G2 = G_pred_latents(model_options(size=64, renderer_spatial_output_dim=16), rendering_options())
+    e0 = _lib.pack_epoch
+    G.load_state_dict(G2.state_dict())
+    e1 = _lib.pack_epoch
+    G.eval()
+    e2 = _lib.pack_epoch
+    G.float()
+    e3 = _lib.pack_epoch
+    e3dge_b200.accumulate(G, G2, decay=0.5)
+    e4 = _lib.pack_epoch
+    e3dge_b200.invalidate_packed()
+    assert e0 < e1 < e2 < e3 < e4 < _lib.pack_epoch
+    # accumulate() is the reference's EMA (training_utils.py:40-45)
+    for p, q in zip(G.parameters(), G2.parameters()):
+        assert torch.equal(p, q)  # both started from G2's weights: the average of equals stays equal
+
+
+def test_ctypes_layer_bookkeeping():
+    from e3dge_b200 import _lib
+    assert all(isinstance(v, int) for v in _lib.KERNELS_PER_CALL.values())
+    assert set(_lib.KERNELS_PER_CALL) <= set(_lib._PROTOTYPES)
+
+    class Fake:  # stands in for tensors of two devices
+        def __init__(self, idx):
+            self.device = type("D", (), {"index": idx})()
+    _lib._tls.dev = None
+    _lib._note_device(Fake(1))
+    _lib._note_device(Fake(1))
+    assert _lib._tls.dev == 1
+    import pytest
+    with pytest.raises(RuntimeError, match="different devices"):
+        _lib._note_device(Fake(0))
+    assert _lib._tls.dev is None
