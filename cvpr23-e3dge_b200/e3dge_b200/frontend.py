@@ -24,14 +24,20 @@ from .stylesdf_model import EqualLinear
 
 
 # ---------------------------------------------------------------------------------------- cameras
-def generate_camera_params(resolution, device, batch=1, locations=None, uniform=False, azim_range=0.3,
+def generate_camera_params(resolution, device, batch=1, locations=None, sweep=False, uniform=False, azim_range=0.3,
                            elev_range=0.15, fov_ang=6, dist_radius=0.12, return_calibs=False, azim_mean=0.,
                            elev_mean=0., generator=None):
-    """Cameras on the unit sphere looking at the origin — camera_utils.py:8-151 (`sweep` mode not provided).
-    locations [B,2] = (azimuth, elevation) in radians, else sampled (normal, or uniform in +-range)."""
+    """Cameras on the unit sphere looking at the origin — camera_utils.py:8-151.
+    locations [B,2] = (azimuth, elevation) in radians; else `sweep` = 8 evenly spaced azimuths per identity at one
+    random elevation each (8*batch cameras); else sampled (normal, or uniform in +-range)."""
     if locations is not None:
         azim, elev = locations[:, 0:1], locations[:, 1:2]
         batch = azim.shape[0]
+    elif sweep:
+        azim = (-azim_range + (2 * azim_range / 7) * torch.arange(8, device=device)).reshape(-1, 1).repeat(batch, 1)
+        elev = (-elev_range + 2 * elev_range *
+                torch.rand(batch, 1, device=device, generator=generator).repeat(1, 8).reshape(-1, 1))
+        batch = batch * 8
     elif uniform:
         azim = -azim_range + 2 * azim_range * torch.rand(batch, 1, device=device, generator=generator)
         elev = -elev_range + 2 * elev_range * torch.rand(batch, 1, device=device, generator=generator)

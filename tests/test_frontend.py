@@ -55,3 +55,14 @@ def test_camera_params_match_the_reference_fixture():
     p, f, n, fr, v = generate_camera_params(64, torch.device("cpu"), 16, generator=torch.Generator().manual_seed(1))
     assert torch.allclose(p[:, :, 3].norm(dim=1), torch.ones(16), atol=1e-6)
     assert torch.allclose(torch.det(p[:, :, :3]), torch.ones(16), atol=1e-5)
+
+
+def test_camera_sweep_mode():
+    """camera_utils.py:36-52: 8 azimuths from -range to +range per identity, one elevation per identity."""
+    from e3dge_b200.frontend import generate_camera_params
+    cams = generate_camera_params(64, torch.device("cpu"), 3, sweep=True, return_calibs=True,
+                                  generator=torch.Generator().manual_seed(2))
+    vp = cams["viewpoint"].reshape(3, 8, 2)
+    assert cams["poses"].shape == (24, 3, 4) and cams["calibs"].shape == (24, 4, 4) and cams["focal"].shape == (24, 1, 1)
+    assert torch.allclose(vp[:, :, 0], torch.linspace(-0.3, 0.3, 8).expand(3, 8), atol=1e-6)
+    assert (vp[:, :, 1] == vp[:, :1, 1]).all() and (vp[:, 0, 1].abs() <= 0.15).all()

@@ -110,3 +110,80 @@ print('RESULT' + json.dumps({'eik': rel_linf(e2.detach(), eik.detach()), 'grad':
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.split("RESULT")[-1])
     assert res["gmax"] > 0 and res["eik"] < 2e-5 and res["grad"] < 1e-4, res
+
+
+def test_call_signatures_of_the_mirrored_api_match_the_live_reference():
+    """Drop-in boundary: every parameter the reference's callers can pass by name exists here under
+    the same name, in the same position, with the same default — checked against the reference's own classes."""
+    script = r"""
+import inspect, json, os, sys
+import numpy as np
+np.deprecate = lambda f=None, *a, **k: (f if callable(f) else (lambda g: g))
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/cvpr23-e3dge_b200')
+import torch
+from oracle import ref_harness as H
+for n in ('munch', 'omegaconf', 'omegaconf.dictconfig', 'IPython', 'IPython.display'):
+    H._stub_module(n)
+ref = H.load_reference()
+H._shell_package('project.models.helper_modules', os.path.join(H.REFERENCE_ROOT, 'project', 'models', 'helper_modules'))
+H._shell_package('project.models.encoders', os.path.join(H.REFERENCE_ROOT, 'project', 'models', 'encoders'))
+from project.models.helper_modules import sft as r_sft, resnetfc as r_res, helpers as r_help
+from project.models.encoders import fpn_encoders as r_enc
+from project.utils import misc_utils as r_misc, camera_utils as r_cam
+import e3dge_b200.volume_renderer as vr, e3dge_b200.stylesdf_model as sm, e3dge_b200.local_branch as lb
+import e3dge_b200.frontend as fe, e3dge_b200.op as op
+rv, rs = ref.volume_renderer, ref.stylesdf_model
+pairs = [
+    (rs.G_pred_latents, sm.G_pred_latents, ['__init__', 'forward']),
+    (rs.Generator, sm.Generator, ['__init__', 'forward', 'mean_latent', 'styles_and_noise_forward']),
+    (rs.Decoder, sm.Decoder, ['__init__', 'forward', 'styles_and_noise_forward']),
+    (rs.StyledConv, sm.StyledConv, ['__init__', 'forward']),
+    (rs.ToRGB, sm.ToRGB, ['__init__', 'forward']),
+    (rs.ModulatedConv2d, sm.ModulatedConv2d, ['__init__', 'forward']),
+    (rs.EqualLinear, sm.EqualLinear, ['__init__', 'forward']),
+    (rv.VolumeFeatureRenderer, vr.VolumeFeatureRenderer, ['__init__', 'forward', 'render', 'run_network', 'get_rays']),
+    (rv.SirenGenerator, vr.SirenGenerator, ['__init__']),
+    (rv.SirenLocalGlobal, vr.SirenLocalGlobal, ['forward', 'forward_backbone', 'retrieve_feats_for_rendering',
+                                                'forward_rendering', 'forward_local']),
+    (rv.FiLMSiren, vr.FiLMSiren, ['__init__', 'forward']),
+    (rv.LinearLayer, vr.LinearLayer, ['__init__', 'forward']),
+    (r_sft.Fuse_sft_MLP, lb.Fuse_sft_MLP, ['__init__', 'forward']),
+    (r_res.ResnetBlockFC, lb.ResnetBlockFC, ['__init__', 'forward']),
+    (r_misc.PosEncoding, lb.PosEncoding, ['__init__', 'forward']),
+    (r_enc.HybridGradualStyleEncoder_V2, fe.HybridGradualStyleEncoder_V2, ['__init__', 'forward']),
+    (r_help.GradualStyleBlock, fe.GradualStyleBlock, ['__init__', 'forward']),
+    (rs.VolumeRenderDiscriminator, fe.VolumeRenderDiscriminator, ['__init__', 'forward']),
+]
+funcs = [(r_cam.generate_camera_params, fe.generate_camera_params),
+         (sys.modules['project.models.op.fused_act'].fused_leaky_relu, op.fused_leaky_relu),
+         (sys.modules['project.models.op.upfirdn2d'].upfirdn2d, op.upfirdn2d)]
+problems = []
+def compare(name, rf, of):
+    rp, opar = inspect.signature(rf).parameters, inspect.signature(of).parameters
+    ours = list(opar)
+    has_kw = any(p.kind == p.VAR_KEYWORD for p in opar.values())
+    for i, (k, p) in enumerate(rp.items()):
+        if p.kind in (p.VAR_POSITIONAL, p.VAR_KEYWORD):
+            continue
+        if k not in opar:
+            if not has_kw:
+                problems.append(f'{name}: parameter {k!r} missing')
+            continue
+        if ours.index(k) != i and p.kind != p.KEYWORD_ONLY:
+            problems.append(f'{name}: parameter {k!r} at position {ours.index(k)} (reference {i})')
+        d, od = p.default, opar[k].default
+        if d is not inspect._empty and not (od is not inspect._empty and (d == od or (d != d and od != od))):
+            if isinstance(d, (int, float, bool, str, type(None), tuple, list)):
+                problems.append(f'{name}: default of {k!r} is {od!r} (reference {d!r})')
+for rc, oc, methods in pairs:
+    for m in methods:
+        compare(f'{oc.__name__}.{m}', getattr(rc, m), getattr(oc, m))
+for rf, of in funcs:
+    compare(of.__name__, rf, of)
+print('RESULT' + json.dumps(problems))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600,
+                         cwd=rh.REFERENCE_ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    problems = json.loads(out.stdout.split("RESULT")[-1])
+    assert not problems, "\n".join(problems)
