@@ -697,7 +697,9 @@ def cpu_baseline(sd, inp, steps=2, frames_per_step=BATCH):
 
 
 def run_reference(args):
-    """Reference arm: the CPU implementation of the path on the box's host cores."""
+    """Reference arm: the CPU implementation of the path on the box's host cores (the oracle port of the
+    reference's PyTorch code — the Python reference itself cannot travel to the GPU box), on the SAME workload as
+    the product arm: one step = the whole batch of 8 frames through renderer + decoder."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -707,28 +709,28 @@ def run_reference(args):
     from oracle import stylesdf_oracle as O
     cores = best_cpu_threads(sd, inp)
     torch.set_num_threads(cores)
-    sl = {k: v[:1] for k, v in inp.items()}  # bounded sample: one frame of the batch per step
 
     def one():
         with torch.no_grad():
-            O.generator_forward(sd, sl["w"], sl["w_dec"], sl["cam_poses"], sl["focal"], sl["near"],
-                                sl["far"], res=RES, n_samples=N_SAMPLES)
+            O.generator_forward(sd, inp["w"], inp["w_dec"], inp["cam_poses"], inp["focal"], inp["near"],
+                                inp["far"], res=RES, n_samples=N_SAMPLES)
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         one()
     dt = time.perf_counter() - t0
-    value = args.steps / dt
-    sample = (f"1 frame of the batch-8 workload per step, fp32, torch CPU {torch.__version__}, "
-              f"{cores} threads (best of 8/16/32/64 on this host; {os.cpu_count()} hardware threads present)")
+    value = args.steps * BATCH / dt
+    sample = (f"the whole batch of {BATCH} frames per step (same workload as the product arm), fp32, torch CPU "
+              f"{torch.__version__}, {cores} threads (best of 8/16/32/64 on this host; {os.cpu_count()} hardware "
+              f"threads present)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (torch CPU)", "data": "synthetic (random latents/cameras, random-init weights)",
         "config": {"workload": WORKLOAD, "size": SIZE, "render_res": RES, "n_samples": N_SAMPLES,
-                   "batch_per_gpu": BATCH},
+                   "batch_per_gpu": BATCH, "global_batch": BATCH},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
