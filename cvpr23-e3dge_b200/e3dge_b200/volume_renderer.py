@@ -5,8 +5,9 @@ follow the reference (project/utils/volume_renderer.py:23-166, 636-749, 1865-197
 its runners can call this module unchanged; the arithmetic between `forward()` and the
 returned dict is ONE CUDA kernel (csrc/render_siren.cu) instead of ~150 ATen launches.
 
-Not provided (SURVEY.md §8 out of scope / "next" rows): marching-cubes mesh extraction
-(`return_mesh`), the 2-D hourglass image filter of the PIFu `netLocal` (an encoder; its per-sample
+Not provided (SURVEY.md §8 out of scope / "next" rows): a GPU surface extractor (`return_mesh`
+aligns the SDF volume on the device and hands it to scikit-image on the host, as the reference does:
+mesh_utils.py), the 2-D hourglass image filter of the PIFu `netLocal` (an encoder; its per-sample
 half — feature query, SFT fusion, positional encoding, texture-modulation MLP — is local_query.py /
 local_branch.py).  Second-order gradients: the eikonal terms carry a graph to the latents (eikonal.py);
 nothing else is twice differentiable.
@@ -775,8 +776,6 @@ class VolumeFeatureRenderer(nn.Module):
     def render(self, focal, c2w, near, far, styles, return_eikonal=False, return_mesh=False,
                mesh_with_shading=True, **kwargs):
         """volume_renderer.py:1666-1701."""
-        if return_mesh:
-            raise NotImplementedError("marching-cubes mesh extraction is out of scope (SURVEY.md §8f)")
         B, dev = c2w.shape[0], c2w.device
         zj = self._make_z_jitter(near, far, B, dev) if (self.perturb and self.perturb > 0) else None
         local_mod = kwargs.get("local_tex_modulation")
@@ -814,6 +813,18 @@ class VolumeFeatureRenderer(nn.Module):
             "depth": o["depth"] if self.return_xyz else None, "mesh": None, "shading_mesh": None,
             "debug_mesh": None, "viewdirs": o["viewdirs"],
         }
+        if return_mesh:
+            # volume_renderer.py:1703-1727: frustum-aligned SDF volume -> marching cubes on the host (skimage,
+            # like the reference; mesh_utils.py raises ImportError when it is not installed).  Batch 1 only (:1736).
+            from .mesh_utils import align_volume, extract_mesh_with_marching_cubes
+            out.pop("shading_mesh"), out.pop("debug_mesh")
+            try:
+                mesh, verts, faces = extract_mesh_with_marching_cubes(align_volume(o["sdf"].detach()))
+                out["mesh"], out["shaded_mesh"] = mesh, mesh
+            except ValueError:  # no zero crossing in the volume
+                print("Marching cubes extraction failed.")
+                print("Please check whether the SDF values are all larger (or all smaller) than 0.")
+                out["mesh"], out["shaded_mesh"] = None, None
         if want_taps:
             out["all_feats"] = list(o["all_feats"].unbind(0))
         if kwargs.get("sample_without_grad", False):

@@ -187,3 +187,34 @@ print('RESULT' + json.dumps(problems))
     assert out.returncode == 0, out.stderr[-3000:]
     problems = json.loads(out.stdout.split("RESULT")[-1])
     assert not problems, "\n".join(problems)
+
+
+def test_align_volume_matches_the_live_reference():
+    """the frustum alignment of the SDF volume, project/utils/mesh_utils.py:17-44."""
+    script = r"""
+import json, sys, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/cvpr23-e3dge_b200')
+from oracle import ref_harness as H
+H.load_reference()
+for n in ('scipy.spatial',):
+    pass
+import importlib.util, os
+spec = importlib.util.spec_from_file_location('ref_mesh_utils', os.path.join(H.REFERENCE_ROOT, 'project', 'utils', 'mesh_utils.py'))
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+from e3dge_b200.mesh_utils import align_volume
+g = torch.Generator().manual_seed(0)
+res = {}
+for shape, near, far in (((1, 12, 10, 7, 1), 0.88, 1.12), ((1, 16, 16, 24, 1), 0.8, 1.3)):
+    v = torch.randn(*shape, generator=g)
+    a, b = m.align_volume(v.clone(), near, far), align_volume(v, near, far)
+    res[str(shape)] = float((a - b).abs().max())
+v = torch.randn(3, 8, 8, 6, 2, generator=g)   # batched, two channels: slice by slice the batch-1 result
+b = align_volume(v)
+res['batched'] = max(float((m.align_volume(v[i:i + 1, ..., c:c + 1].clone()) - b[i:i + 1, ..., c:c + 1]).abs().max())
+                     for i in range(3) for c in range(2))
+print('RESULT' + json.dumps(res))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.split("RESULT")[-1])
+    assert all(v < 1e-6 for v in res.values()), res
