@@ -361,6 +361,11 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if gather_in_graph:  # NCCL waits at teardown for graphs that captured its kernels: drop ours first
+            import gc
+            gcall = None
+            gc.collect()
+            torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
