@@ -142,3 +142,41 @@ def test_ctypes_layer_bookkeeping():
     with pytest.raises(RuntimeError, match="different devices"):
         _lib._note_device(Fake(0))
     assert _lib._tls.dev is None
+
+
+def test_render_host_control_flow_without_a_device(monkeypatch):
+    """The Python half of VolumeFeatureRenderer.render / forward (dict contract of volume_renderer.py:1694-1729,
+    1865-1972) with the kernel call stubbed out: key set, optional entries, and the surface path handing the
+    frustum-aligned SDF volume to the host extractor (ImportError here: scikit-image is not installed)."""
+    import importlib.util
+    from e3dge_b200 import rendering_options
+    from e3dge_b200.volume_renderer import VolumeFeatureRenderer
+    R = VolumeFeatureRenderer(rendering_options(N_samples=6), out_im_res=8).eval()
+    B, n, S = 1, 8, 6
+
+    def fake_raw(self, styles, cam_poses, focal, near, far, z_jitter=None, local_mod=None, flags_over=None,
+                 want_taps=False, film=None, train=False):
+        z = lambda *s: torch.zeros(*s)
+        o = dict(features=z(B, 256, n, n), gen_thumb_imgs=z(B, 3, n, n), xyz=z(B, 3, n, n), mask=z(B, 1, n, n, 1),
+                 depth=z(B, n, n, 1, 1), sdf=torch.linspace(-1, 1, S).expand(B, n, n, S).unsqueeze(-1).clone(),
+                 hit_prob=z(B, n, n, S, 1), visibility=z(B, n, n, S, 1), dists=z(B, n, n, S), points=z(B, n, n, S, 3),
+                 rays_o=z(B, n, n, 3), rays_d=z(B, n, n, 3), viewdirs=z(B, n, n, 3), raw_rgb=z(B, n, n, S, 3))
+        o["near"], o["far"] = z(B, n, n, 1), z(B, n, n, 1)
+        return o
+    monkeypatch.setattr(VolumeFeatureRenderer, "_render_raw", fake_raw)
+    cam = torch.eye(4)[:3].unsqueeze(0)
+    args = (cam, torch.full((B, 1, 1), 300.), torch.full((B, 1, 1), 0.88), torch.full((B, 1, 1), 1.12))
+    with torch.no_grad():
+        out = R(*args, styles=torch.zeros(B, 256))
+    want = {"rays_o", "rays_d", "dists", "near", "far", "hit_prob", "surface_eikonal_term", "points", "sdf",
+            "gen_thumb_imgs", "features", "mask", "xyz", "eikonal_term", "depth", "mesh", "shading_mesh", "debug_mesh",
+            "viewdirs"}
+    assert set(out) == want and out["mesh"] is None and out["eikonal_term"] is None
+    have_skimage = importlib.util.find_spec("skimage") is not None
+    with torch.no_grad():
+        if have_skimage:
+            m = R(*args, styles=torch.zeros(B, 256), return_mesh=True)
+            assert m["mesh"] is not None and "shaded_mesh" in m
+        else:
+            with pytest.raises(ImportError, match="scikit-image"):
+                R(*args, styles=torch.zeros(B, 256), return_mesh=True)
