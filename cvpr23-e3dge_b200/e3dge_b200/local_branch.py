@@ -24,6 +24,13 @@ from . import _lib
 from . import local_query as _lq
 
 
+def _require_cuda(t):
+    """The local branch has no CPU path either: its modules run the fused kernel (inference) or device-side
+    PyTorch (training, autograd) on CUDA tensors only."""
+    if not t.is_cuda:
+        raise RuntimeError("e3dge_b200: CUDA tensor required (this framework has no CPU path)")
+
+
 class ResnetBlockFC(nn.Module):
     """x_s + fc_1(relu(fc_0(relu(x)))) — project/models/helper_modules/resnetfc.py:10-62."""
 
@@ -48,6 +55,7 @@ class ResnetBlockFC(nn.Module):
             nn.init.kaiming_normal_(self.shortcut.weight, a=0, mode="fan_in")
 
     def forward(self, x):
+        _require_cuda(x)
         if (self.size_in, self.size_out) == (301, 512) and _fused_ok(x, self):
             a, b = tex_modulation(self, x)
             return torch.cat([a, b], -1)
@@ -66,6 +74,7 @@ class Fuse_sft_MLP(nn.Module):
         self.shift = nn.Sequential(nn.Linear(out_ch, out_ch), nn.LeakyReLU(0.2, True), nn.Linear(out_ch, out_ch))
 
     def forward(self, enc_feat, dec_feat, w=1):
+        _require_cuda(dec_feat)
         enc_feat = self.encode_enc(torch.cat([enc_feat, dec_feat], dim=-1))
         scale = self.scale(enc_feat)
         shift = self.shift(enc_feat)

@@ -180,3 +180,14 @@ def test_render_host_control_flow_without_a_device(monkeypatch):
         else:
             with pytest.raises(ImportError, match="scikit-image"):
                 R(*args, styles=torch.zeros(B, 256), return_mesh=True)
+
+
+def test_local_branch_modules_have_no_cpu_path():
+    from e3dge_b200.local_branch import Fuse_sft_MLP, ResnetBlockFC, local_tex_modulation
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ResnetBlockFC(301, 512)(torch.zeros(2, 301))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Fuse_sft_MLP(257, 256)(torch.zeros(2, 257), torch.zeros(2, 256))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        local_tex_modulation(Fuse_sft_MLP(257, 256), ResnetBlockFC(301, 512), torch.zeros(2, 257), torch.zeros(2, 256),
+                             torch.zeros(2, 3))
