@@ -170,3 +170,16 @@ def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
     if not input.is_cuda:
         raise RuntimeError("e3dge_b200.upfirdn2d: CUDA tensor required (no CPU path)")
     return _UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+
+
+# ---- op-level route: the reference's own Python wrappers over this library ----------
+# The reference JIT-builds two pybind modules at import (`fused = load("fused", ...)`, fused_act.py:10-16;
+# `upfirdn2d_op = load("upfirdn2d", ...)`, upfirdn2d.py:9-15).  These two objects have their call shapes
+# (fused_bias_act.cpp:11-20, upfirdn2d.cpp:12-23), so a maintainer replaces the two `load(...)` calls by
+# `from e3dge_b200.op import fused` / `upfirdn2d_op` and keeps every line of the reference's autograd code.
+class fused:
+    fused_bias_act = staticmethod(_bias_act)
+
+
+class upfirdn2d_op:
+    upfirdn2d = staticmethod(_upfirdn2d_raw)

@@ -218,3 +218,79 @@ print('RESULT' + json.dumps(res))
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads(out.stdout.split("RESULT")[-1])
     assert all(v < 1e-6 for v in res.values()), res
+
+
+def test_reference_op_wrappers_drive_the_op_level_stubs():
+    """INTEGRATION.md §2, exercised: the reference's OWN autograd wrappers (op/fused_act.py, op/upfirdn2d.py) are
+    loaded with `load(...)` returning this library's `fused` / `upfirdn2d_op` objects.  No GPU here, so the two
+    entry points are replaced by CPU stand-ins with the SAME Python signatures (checked) that record how the
+    reference calls them: argument order, the empty-tensor conventions, act / grad codes — forward, backward and
+    double backward — and the results are held to autograd through the closed-form op."""
+    script = r"""
+import inspect, json, os, sys, types, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/cvpr23-e3dge_b200')
+from oracle import ref_harness as H, stylesdf_oracle as O
+import torch.utils.cpp_extension as ce
+import e3dge_b200.op as op
+calls = []
+class fake_fused:
+    @staticmethod
+    def fused_bias_act(x, bias, refer, act, grad, alpha, scale):
+        calls.append(('fused', tuple(x.shape), int(bias.numel()), int(refer.numel()), act, grad))
+        assert act == 3 and grad in (0, 1)
+        v = x + bias.reshape(1, -1, *([1] * (x.ndim - 2))) if bias.numel() else x
+        gate = (refer if grad == 1 else v) > 0
+        return torch.where(gate, v, v * alpha) * scale
+class fake_up:
+    @staticmethod
+    def upfirdn2d(x4, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+        calls.append(('up', tuple(x4.shape), up_x, down_x, pad_x0, pad_x1))
+        assert x4.ndim == 4 and x4.shape[-1] == 1 and up_x == up_y and down_x == down_y
+        y = O.upfirdn2d(x4.permute(0, 3, 1, 2), kernel, up=up_x, down=down_x, pad=(pad_x0, pad_x1)) \
+            if (pad_x0, pad_x1) == (pad_y0, pad_y1) else None
+        return y.permute(0, 2, 3, 1).contiguous()
+sig = lambda f: list(inspect.signature(f).parameters)
+assert sig(fake_fused.fused_bias_act) == sig(op.fused.fused_bias_act), (sig(fake_fused.fused_bias_act), sig(op.fused.fused_bias_act))
+assert sig(fake_up.upfirdn2d) == sig(op.upfirdn2d_op.upfirdn2d)
+real_load = ce.load
+ce.load = lambda name, **kw: {'fused': op.fused, 'upfirdn2d': op.upfirdn2d_op}[name]
+try:
+    def load_module(fname):
+        spec = __import__('importlib.util').util.spec_from_file_location(
+            'ref_' + fname, os.path.join(H.REFERENCE_ROOT, 'project', 'models', 'op', fname + '.py'))
+        m = __import__('importlib.util').util.module_from_spec(spec); spec.loader.exec_module(m); return m
+    fa, up = load_module('fused_act'), load_module('upfirdn2d')
+finally:
+    ce.load = real_load
+res = {'bound': fa.fused is op.fused and up.upfirdn2d_op is op.upfirdn2d_op}
+fa.fused, up.upfirdn2d_op = fake_fused, fake_up      # same signatures, CPU arithmetic
+g = torch.Generator().manual_seed(0)
+x = torch.randn(2, 4, 5, 5, generator=g, dtype=torch.float64, requires_grad=True)
+b = torch.randn(4, generator=g, dtype=torch.float64, requires_grad=True)
+ref_fn = lambda x, b: torch.nn.functional.leaky_relu(x + b.reshape(1, -1, 1, 1), 0.2) * 2 ** 0.5
+y = fa.FusedLeakyReLUFunction.apply(x, b, 0.2, 2 ** 0.5)
+ct = torch.randn(y.shape, generator=g, dtype=torch.float64)
+gx, gb = torch.autograd.grad((y * ct).sum(), [x, b], create_graph=True)
+rx, rb = torch.autograd.grad((ref_fn(x, b) * ct).sum(), [x, b], create_graph=True)
+ggx, = torch.autograd.grad((gx * ct).sum() + gb.sum(), [x], allow_unused=True)
+res['fused'] = max(float((y - ref_fn(x, b)).abs().max()), float((gx - rx).abs().max()), float((gb - rb).abs().max()))
+k = torch.tensor([1., 3., 3., 1.], dtype=torch.float64); k = k[None] * k[:, None]; k = k / k.sum()
+xi = torch.randn(2, 3, 8, 8, generator=g, dtype=torch.float64, requires_grad=True)
+errs = []
+for upf, down, pad in ((1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (1, 1))):
+    yo = up.UpFirDn2d.apply(xi, k * upf ** 2, (upf, upf), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+    yr = O.upfirdn2d(xi, k * upf ** 2, up=upf, down=down, pad=pad)
+    c2 = torch.randn(yo.shape, generator=g, dtype=torch.float64)
+    go, = torch.autograd.grad((yo * c2).sum(), [xi], create_graph=True)
+    gr, = torch.autograd.grad((yr * c2).sum(), [xi])
+    ggo, = torch.autograd.grad((go * go.detach()).sum(), [c2.requires_grad_(True)], allow_unused=True) if False else (None,)
+    errs += [float((yo - yr).abs().max()), float((go - gr).abs().max())]
+res['upfirdn2d'] = max(errs)
+res['calls'] = calls[:4] + [len(calls)]
+print('RESULT' + json.dumps(res))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.split("RESULT")[-1])
+    assert res["bound"] and res["fused"] < 1e-12 and res["upfirdn2d"] < 1e-12, res
+    assert res["calls"][-1] >= 9   # fused: fwd + bwd (+ double bwd); upfirdn2d: fwd + bwd for three configurations
