@@ -294,3 +294,60 @@ print('RESULT' + json.dumps(res))
     res = json.loads(out.stdout.split("RESULT")[-1])
     assert res["bound"] and res["fused"] < 1e-12 and res["upfirdn2d"] < 1e-12, res
     assert res["calls"][-1] >= 9   # fused: fwd + bwd (+ double bwd); upfirdn2d: fwd + bwd for three configurations
+
+
+def test_generator_call_sites_of_the_reference_runners_bind_to_this_forward():
+    """Every place the reference's runners and data utilities CALL the generator / renderer
+    (trainer.py:881-896 `latent2image`, :1399 `latent2surface`, data_util.py:74, stylesdf_model.py:965, 1100, ...)
+    is parsed from the reference's source; its positional count and keyword names must bind to this package's
+    `G_pred_latents.forward` / `VolumeFeatureRenderer.forward` signatures."""
+    import ast
+    import inspect
+    proj = os.path.join(rh.REFERENCE_ROOT, "project")
+    sys.path.insert(0, os.path.join(ROOT, "cvpr23-e3dge_b200"))
+    from e3dge_b200.local_branch import LocalBranch
+    from e3dge_b200.stylesdf_model import Decoder, G_pred_latents
+    from e3dge_b200.volume_renderer import SirenGenerator, VolumeFeatureRenderer
+    net_local = "self.g_module.renderer.network.netLocal."
+    targets = {  # callee expression (as written in the reference) -> the method it reaches
+        "generator": G_pred_latents.forward, "self.generator": G_pred_latents.forward,
+        "surface_g_ema": G_pred_latents.forward, "g_ema": G_pred_latents.forward,
+        "self.g_module": G_pred_latents.forward, "self.renderer": VolumeFeatureRenderer.forward,
+        "self.decoder": Decoder.forward, "self.g_module.mean_latent": G_pred_latents.mean_latent,
+        "self.g_module.styles_and_noise_forward": G_pred_latents.styles_and_noise_forward,
+        "self.renderer.mlp_init_pass": VolumeFeatureRenderer.mlp_init_pass,
+        "self.renderer.sdf_sample_pass": VolumeFeatureRenderer.sdf_sample_pass,
+        "self.netGlobal.forward_generator": SirenGenerator.forward_generator,
+        net_local + "query": LocalBranch.query, net_local + "filter": LocalBranch.filter,
+    }
+    files = [os.path.join(proj, "trainers", f) for f in ("trainer.py", "cycle_runner.py", "datasetgan_runner.py")]
+    files += [os.path.join(proj, "trainers", "E3DGE", f) for f in os.listdir(os.path.join(proj, "trainers", "E3DGE"))
+              if f.endswith(".py")]
+    files += [os.path.join(proj, "utils", f) for f in ("data_util.py", "volume_renderer.py")]
+    files += [os.path.join(proj, "models", "stylesdf_model.py")]
+    checked, problems = 0, []
+    for path in files:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", SyntaxWarning)  # the reference has a few '\p' in docstrings
+            tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.Call):
+                continue
+            callee = ast.unparse(node.func)
+            if callee not in targets:
+                continue
+            params = inspect.signature(targets[callee]).parameters
+            names = [n for n in params if n != "self"]
+            has_kwargs = any(p.kind == p.VAR_KEYWORD for p in params.values())
+            n_pos = len([a for a in node.args if not isinstance(a, ast.Starred)])
+            if n_pos > len(names):
+                problems.append(f"{path}:{node.lineno} {callee}: {n_pos} positional arguments")
+            for kw in node.keywords:
+                if kw.arg is not None and kw.arg not in names and not has_kwargs:
+                    problems.append(f"{path}:{node.lineno} {callee}: keyword {kw.arg!r} not accepted")
+                if kw.arg is not None and kw.arg in names[:n_pos]:
+                    problems.append(f"{path}:{node.lineno} {callee}: {kw.arg!r} given twice")
+            checked += 1
+    assert checked >= 15, checked
+    assert not problems, "\n".join(problems)
