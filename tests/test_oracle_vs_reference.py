@@ -351,3 +351,32 @@ def test_generator_call_sites_of_the_reference_runners_bind_to_this_forward():
             checked += 1
     assert checked >= 15, checked
     assert not problems, "\n".join(problems)
+
+
+def test_local_model_state_dict_is_the_reference_minus_the_image_filter():
+    """`--enable_local_model`: this package's renderer state_dict = the reference's (same names, same shapes) minus
+    the 2-D hourglass filter of netLocal, which is an encoder the caller attaches."""
+    script = r"""
+import json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/cvpr23-e3dge_b200'); sys.path.insert(0, %(root)r + '/oracle')
+import gen_golden_local_mlp as gen
+ref, _, _ = gen.load()
+R = ref.volume_renderer.VolumeFeatureRenderer(gen.local_rendering_opt(), style_dim=256, out_im_res=8)
+theirs = {k: tuple(v.shape) for k, v in R.state_dict().items()}
+from e3dge_b200 import rendering_options
+from e3dge_b200.volume_renderer import VolumeFeatureRenderer
+mine = VolumeFeatureRenderer(rendering_options(enable_local_model=True, local_modulation_layer=True,
+                                               L_pred_tex_modulations=True, residual_local_feats_dim=301), out_im_res=8)
+ours = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+missing = sorted(k for k in theirs if k not in ours)
+res = {'subset': all(k in theirs and theirs[k] == s for k, s in ours.items()), 'n_ours': len(ours),
+       'missing_prefixes': sorted({'.'.join(k.split('.')[:3]) for k in missing})}
+print('RESULT' + json.dumps(res))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.split("RESULT")[-1])
+    assert res["subset"] and res["n_ours"] > 60, res
+    assert set(res["missing_prefixes"]) <= {"network.netLocal.image_filter", "network.netLocal.depth_conv",
+                                            "network.netLocal.residual_conv",
+                                            "network.netLocal.downsample_channel_conv"}, res
