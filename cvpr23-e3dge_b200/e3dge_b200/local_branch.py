@@ -104,12 +104,19 @@ class LocalBranch(nn.Module):
     """`netLocal` of SirenLocalGlobal: the part of the reference's HGPIFuNetGANResidualResnetFC
     (vendor/pifu/lib/model/HGPIFuGANNetResidualInputResnetFC.py:19-97) that runs per sample —
     `query` (pixel-aligned feature gather, csrc/local_query.cu) and `local_feat_to_tex_modulations_linear`
-    (zero-initialised ResnetBlockFC(301, 512), :84-97).  The 2-D hourglass `filter` that produces the feature
-    map is an image encoder (out of scope); `attach_filter(module)` plugs the caller's in."""
+    (zero-initialised ResnetBlockFC(301, 512), :84-97) — plus, when the PIFu option group is given, the 2-D
+    `filter` (residual / depth stems + stacked hourglass, local_filter.py: PyTorch / cuDNN library code under the
+    reference's parameter names).  Without it `attach_filter(module)` plugs the caller's filter in."""
 
-    def __init__(self, opt=None):
+    def __init__(self, opt=None, local_options=None):
         super().__init__()
         self.opt = opt
+        # the 2-D image filter (hourglass + stems) under the reference's names, when the PIFu option group is given
+        # (`opt.pifu`, volume_renderer.py:741): library-code conv nets, see local_filter.py
+        self.local_options = local_options
+        if local_options is not None:
+            from .local_filter import build_filter_modules
+            build_filter_modules(self, local_options)
         dim = int(getattr(opt, "residual_local_feats_dim", 301)) if opt is not None else 301
         if opt is None or getattr(opt, "L_pred_tex_modulations", True):
             m = ResnetBlockFC(dim, 256 * 2)
@@ -129,11 +136,17 @@ class LocalBranch(nn.Module):
 
     def filter(self, residual_images, depth_feat=None, ref_feats=None, feat_key="ref_view", return_feat=False,
                *args, **kwargs):
-        if self.image_filter_module is None:
-            raise NotImplementedError("the hourglass image filter of netLocal is an encoder (out of scope, SURVEY.md "
-                                      "§8); attach the caller's with LocalBranch.attach_filter(module)")
-        feat = self.image_filter_module(residual_images, depth_feat=depth_feat, ref_feats=ref_feats, **kwargs)
-        feats = list(feat) if isinstance(feat, (list, tuple)) else [feat]
+        if self.image_filter_module is not None:  # a caller-attached filter takes precedence
+            feat = self.image_filter_module(residual_images, depth_feat=depth_feat, ref_feats=ref_feats, **kwargs)
+            feats = list(feat) if isinstance(feat, (list, tuple)) else [feat]
+        elif self.local_options is not None:
+            from .local_filter import run_filter
+            outputs, self.tmpx, self.normx = run_filter(self, residual_images, depth_feat, ref_feats)
+            feats = [outputs[-1]]  # only the last stack is kept (HGPIFuNet.py:91-97)
+        else:
+            raise NotImplementedError("netLocal was built without its image filter (no `pifu` option group in the "
+                                      "rendering options); pass one, or attach the caller's filter with "
+                                      "LocalBranch.attach_filter(module)")
         self.im_feat_dict[feat_key] = feats
         return feats if return_feat else None
 

@@ -222,7 +222,7 @@ class SirenLocalGlobal(nn.Module):
         self.opt = opt
         self.netGlobal = SirenGenerator(opt, D, W, style_dim, input_ch, input_ch_views, output_ch,
                                         output_features, scene_scale)
-        self.netLocal = LocalBranch(opt)
+        self.netLocal = LocalBranch(opt, local_options)
 
     def forward_local(self, data_batch):
         """:439-476 — local features of the sample points: given (`feats`) or queried from filtered images."""
@@ -516,9 +516,10 @@ class VolumeFeatureRenderer(nn.Module):
         self.grid_un_warper = UniformBoxWarp(1 / opt.camera.dist_radius * 2)
         self.enable_local_model = bool(opt.enable_local_model)
         net_cls = SirenLocalGlobal if self.enable_local_model else SirenGenerator
+        extra = {"local_options": getattr(opt, "pifu", None)} if self.enable_local_model else {}  # :741
         self.network = net_cls(opt=opt, D=opt.depth, W=opt.width, style_dim=style_dim,
                                input_ch=3, output_ch=4, input_ch_views=3,
-                               output_features=self.output_features)
+                               output_features=self.output_features, **extra)
         r = opt.camera.dist_radius
         self.register_buffer("B_MAX", torch.Tensor([r] * 3), persistent=False)
         self.register_buffer("B_MIN", -torch.Tensor([r] * 3), persistent=False)

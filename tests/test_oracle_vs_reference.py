@@ -380,3 +380,43 @@ print('RESULT' + json.dumps(res))
     assert set(res["missing_prefixes"]) <= {"network.netLocal.image_filter", "network.netLocal.depth_conv",
                                             "network.netLocal.residual_conv",
                                             "network.netLocal.downsample_channel_conv"}, res
+
+
+def test_netlocal_image_filter_matches_the_live_reference():
+    """With the PIFu option group given, netLocal is complete: the renderer's state_dict equals the reference's
+    `--enable_local_model` one key for key (456 netLocal entries, 15.3 M parameters) and loads it strictly, and
+    `netLocal.filter` (residual / depth stems + 4-stack hourglass, local_filter.py) reproduces the reference's
+    feature map on the same weights and inputs."""
+    script = r"""
+import json, sys, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + '/cvpr23-e3dge_b200'); sys.path.insert(0, %(root)r + '/oracle')
+import gen_golden_local_mlp as gen
+ref, _, _ = gen.load()
+torch.manual_seed(0)
+R = ref.volume_renderer.VolumeFeatureRenderer(gen.local_rendering_opt(), style_dim=256, out_im_res=8).eval()
+from e3dge_b200 import Opt, rendering_options
+from e3dge_b200.volume_renderer import VolumeFeatureRenderer
+mine = VolumeFeatureRenderer(rendering_options(enable_local_model=True, local_modulation_layer=True,
+                                               L_pred_tex_modulations=True, residual_local_feats_dim=301,
+                                               pifu=Opt(gen.pifu_opt())), out_im_res=8).eval()
+theirs = R.state_dict()
+res = {'same_keys': sorted(theirs) == sorted(mine.state_dict()),
+       'same_shapes': all(tuple(theirs[k].shape) == tuple(v.shape) for k, v in mine.state_dict().items() if k in theirs),
+       'n_params': sum(p.numel() for p in mine.network.netLocal.parameters())}
+mine.load_state_dict(theirs, strict=True)
+g = torch.Generator().manual_seed(1)
+img, dep = torch.randn(2, 3, 64, 64, generator=g), torch.randn(2, 1, 64, 64, generator=g)
+with torch.no_grad():
+    a = R.network.netLocal.filter(residual_images=img, depth_feat=dep, ref_feats=None, feat_key='ref_view', return_feat=True)[-1]
+    b = mine.network.netLocal.filter(residual_images=img, depth_feat=dep, ref_feats=None, feat_key='ref_view', return_feat=True)[-1]
+    c = mine.network.netLocal.filter(residual_images=img, feat_key='que_view', return_feat=True) if False else None
+res['shape'] = list(b.shape)
+res['err'] = float((a - b).abs().max() / a.abs().max())
+res['stored'] = len(mine.network.netLocal.im_feat_dict['ref_view'])
+print('RESULT' + json.dumps(res))
+""" % {"root": ROOT}
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.split("RESULT")[-1])
+    assert res["same_keys"] and res["same_shapes"] and res["n_params"] == 15347222, res
+    assert res["shape"] == [2, 256, 16, 16] and res["stored"] == 1 and res["err"] < 1e-5, res
